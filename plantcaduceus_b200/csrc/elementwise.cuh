@@ -1,0 +1,302 @@
+// HBM-bound kernels of the Caduceus forward: tokenise, RC-aware embedding, fused residual-add RMSNorm,
+// depthwise causal conv + SiLU (both scan directions from one read), RC LM head, hidden-state tap.
+//
+// Internal layout ("strand-major"): the B input windows become S = 2B independent sequences,
+//   s <  B : forward strand of window s,                 ids_s[t] = ids[s][t]
+//   s >= B : reverse-complement strand of window s - B,  ids_s[t] = comp[ids[s-B][L-1-t]]
+// stored token-major as [S*L, channels].  In this orientation the RC half of the reference's
+// [B, L, 2d] tensors (which it keeps flipped in sequence AND channel) is an
+// ordinary sequence, so every layer treats both strands identically with the same weights and no flip
+// is ever materialised; the flips reappear only as index arithmetic in embed / lm_head / hidden tap.
+#pragma once
+
+#include "common.cuh"
+
+namespace pcad {
+
+// ---- 8-element vector helpers (one "vec" = 8 consecutive channels, any dtype) -----------------
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    load16<T>(p, v);
+  } else {
+    float a[4], b[4];
+    load16<T>(p, a);
+    load16<T>(p + 4, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = a[i]; v[4 + i] = b[i]; }
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    store16<T>(p, v);
+  } else {
+    float a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
+    store16<T>(p, a);
+    store16<T>(p + 4, b);
+  }
+}
+
+// ---- tokenise -----------------------------------------------------------------------------------
+// ids[i] = lut[ascii[i]]; if mask_pos >= 0, position mask_pos of every window of length L gets mask_id.
+// Replaces tokenizer.encode_plus + ids[0, tokenIdx] = mask_token_id (reference zero_shot_score.py:51-57).
+__global__ void tokenize_kernel(const uint8_t* __restrict__ ascii, uint8_t* __restrict__ ids, long long n,
+                                const uint8_t* __restrict__ lut, int L, int mask_pos, int mask_id) {
+  __shared__ uint8_t s_lut[256];
+  s_lut[threadIdx.x & 255] = lut[threadIdx.x & 255];
+  __syncthreads();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t id = s_lut[ascii[i]];
+  if (mask_pos >= 0 && (i % L) == mask_pos) id = static_cast<uint8_t>(mask_id);
+  ids[i] = id;
+}
+
+__global__ void ids64_to_u8_kernel(const long long* __restrict__ in, uint8_t* __restrict__ out, long long n, int V,
+                                   int* __restrict__ bad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long v = in[i];
+  if (v < 0 || v >= V) { atomicExch(bad, 1); out[i] = 0; return; }
+  out[i] = static_cast<uint8_t>(v);
+}
+
+// ---- RC-aware embedding [EXT RCPSEmbedding.forward] --------------------------------------------
+// out[s*L + t, :] = emb[id_s[t], :]  (see layout note above).  One thread per 8 channels.
+template <typename T>
+__global__ void embed_kernel(const uint8_t* __restrict__ ids, const T* __restrict__ emb, T* __restrict__ out, int B,
+                             int L, int d, const uint8_t* __restrict__ comp) {
+  const int vec_per_row = d / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = 2LL * B * L * vec_per_row;
+  if (gid >= total) return;
+  const int v = static_cast<int>(gid % vec_per_row);
+  const long long row = gid / vec_per_row;
+  const int t = static_cast<int>(row % L);
+  const int s = static_cast<int>(row / L);
+  int id;
+  if (s < B) id = ids[static_cast<long long>(s) * L + t];
+  else id = comp[ids[static_cast<long long>(s - B) * L + (L - 1 - t)]];
+  float x[8];
+  load8<T>(emb + static_cast<long long>(id) * d + v * 8, x);
+  store8<T>(out + row * d + v * 8, x);
+}
+
+// ---- fused residual add + RMSNorm [EXT rms_norm_fn(prenorm=True, residual_in_fp32)] ------------
+// One warp per row.  res_out = x + res_in (fp32 sum, stored as RT); y = sum * rstd * w (stored as T);
+// statistics from the un-rounded fp32 sum, as the reference's Triton kernel does.
+template <typename T, typename RT, int CH>
+__global__ void __launch_bounds__(256)
+add_rmsnorm_kernel(const T* __restrict__ x, const RT* __restrict__ res_in, const float* __restrict__ w,
+                   T* __restrict__ y, RT* __restrict__ res_out, long long rows, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = d >> 3;
+  float v[CH][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int vi = lane + 32 * c;
+    if (vi < nvec) {
+      load8<T>(x + row * d + vi * 8, v[c]);
+      if (res_in != nullptr) {
+        float r[8];
+        load8<RT>(res_in + row * d + vi * 8, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] += r[i];
+      }
+      if (res_out != nullptr) store8<RT>(res_out + row * d + vi * 8, v[c]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss = fmaf(v[c][i], v[c][i], ss);
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int vi = lane + 32 * c;
+    if (vi < nvec) {
+      float o[8];
+      const float4 w0 = *reinterpret_cast<const float4*>(w + vi * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w + vi * 8 + 4);
+      o[0] = v[c][0] * rstd * w0.x; o[1] = v[c][1] * rstd * w0.y; o[2] = v[c][2] * rstd * w0.z; o[3] = v[c][3] * rstd * w0.w;
+      o[4] = v[c][4] * rstd * w1.x; o[5] = v[c][5] * rstd * w1.y; o[6] = v[c][6] * rstd * w1.z; o[7] = v[c][7] * rstd * w1.w;
+      store8<T>(y + row * d + vi * 8, o);
+    }
+  }
+}
+
+// ---- depthwise causal conv k=4 + SiLU, both directions [EXT causal_conv1d_fn(activation="silu")] --
+// x: [S*L, *] with row pitch ldx (the x half of xz).  4 channels per thread, TT timesteps per thread,
+// sliding 7-row register window.  out_f[t] = SiLU(b_f + sum_k w_f[k] x[t-3+k]);
+// out_r[t] = SiLU(b_r + sum_k w_r[k] x[t+3-k])  (the causal conv of the time-reversed sequence).
+constexpr int kConvTT = 32;
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4]) {
+  if constexpr (sizeof(T) == 2) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+    v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+  } else {
+    const float4 raw = *reinterpret_cast<const float4*>(p);
+    v[0] = raw.x; v[1] = raw.y; v[2] = raw.z; v[3] = raw.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&v)[4]) {
+  if constexpr (sizeof(T) == 2) {
+    uint2 raw;
+    raw.x = pack_bf16x2(v[0], v[1]);
+    raw.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = raw;
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+template <typename T, bool PRECISE>
+__global__ void __launch_bounds__(128)
+conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ w_f, const float* __restrict__ b_f,
+                 const float* __restrict__ w_r, const float* __restrict__ b_r, T* __restrict__ out_f,
+                 T* __restrict__ out_r, int L, int E) {
+  const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e0 >= E) return;
+  const int t0 = blockIdx.y * kConvTT;
+  const long long seq_row0 = static_cast<long long>(blockIdx.z) * L;
+  float wf[4][4], wr[4][4], bf[4], br[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(w_f + (e0 + c) * 4);
+    const float4 b = *reinterpret_cast<const float4*>(w_r + (e0 + c) * 4);
+    wf[c][0] = a.x; wf[c][1] = a.y; wf[c][2] = a.z; wf[c][3] = a.w;
+    wr[c][0] = b.x; wr[c][1] = b.y; wr[c][2] = b.z; wr[c][3] = b.w;
+    bf[c] = b_f[e0 + c];
+    br[c] = b_r[e0 + c];
+  }
+  // win[j] holds x[t - 3 + j], j = 0..6
+  float win[7][4];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int t = t0 - 3 + j;
+    if (t >= 0 && t < L) load4<T>(x + (seq_row0 + t) * ldx + e0, win[j]);
+    else { win[j][0] = win[j][1] = win[j][2] = win[j][3] = 0.f; }
+  }
+#pragma unroll 4
+  for (int i = 0; i < kConvTT; ++i) {
+    const int t = t0 + i;
+    if (t >= L) break;
+    if (t + 3 < L) load4<T>(x + (seq_row0 + t + 3) * ldx + e0, win[6]);
+    else { win[6][0] = win[6][1] = win[6][2] = win[6][3] = 0.f; }
+    float of[4], orv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float a = bf[c];
+      a = fmaf(wf[c][0], win[0][c], a);
+      a = fmaf(wf[c][1], win[1][c], a);
+      a = fmaf(wf[c][2], win[2][c], a);
+      a = fmaf(wf[c][3], win[3][c], a);
+      of[c] = silu<PRECISE>(a);
+      float r = br[c];
+      r = fmaf(wr[c][0], win[6][c], r);
+      r = fmaf(wr[c][1], win[5][c], r);
+      r = fmaf(wr[c][2], win[4][c], r);
+      r = fmaf(wr[c][3], win[3][c], r);
+      orv[c] = silu<PRECISE>(r);
+    }
+    store4<T>(out_f + (seq_row0 + t) * E + e0, of);
+    store4<T>(out_r + (seq_row0 + t) * E + e0, orv);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) win[j][c] = win[j + 1][c];
+  }
+}
+
+// ---- RC LM head [EXT RCPSLMHead.forward + .float()] ---------------------------------------------
+// logits[b, t, v] = <HF[b, t, :], W[v, :]> + <HR[b, L-1-t, :], W[comp[v], :]>, V = 8, fp32 out.
+// One warp per requested position.  If pos != nullptr only positions pos[b*n_pos + i] are computed and
+// only the 4 columns sel[0..3] (a,c,g,t) are written: out[(b*n_pos + i)*4 + k].
+template <typename T>
+__global__ void __launch_bounds__(256)
+lm_head_kernel(const T* __restrict__ H, const float* __restrict__ W, const uint8_t* __restrict__ comp,
+               const int* __restrict__ pos, int n_pos, const int* __restrict__ sel, float* __restrict__ out, int B,
+               int L, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long item = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_items = pos ? static_cast<long long>(B) * n_pos : static_cast<long long>(B) * L;
+  if (item >= n_items) return;
+  int b, t;
+  if (pos) { b = static_cast<int>(item / n_pos); t = pos[item]; }
+  else { b = static_cast<int>(item / L); t = static_cast<int>(item % L); }
+  if (t < 0 || t >= L) {  // invalid position: write NaN so the caller notices
+    if (lane < 4 && pos) out[item * 4 + lane] = __int_as_float(0x7fc00000);
+    return;
+  }
+  const T* hf = H + (static_cast<long long>(b) * L + t) * d;
+  const T* hr = H + (static_cast<long long>(B + b) * L + (L - 1 - t)) * d;
+  float acc[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) acc[v] = 0.f;
+  for (int j = lane * 8; j < d; j += 256) {
+    float a[8], r[8];
+    load8<T>(hf + j, a);
+    load8<T>(hr + j, r);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const float* wv = W + v * d + j;
+      const float* wc = W + static_cast<int>(comp[v]) * d + j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[v] = fmaf(a[i], wv[i], fmaf(r[i], wc[i], acc[v]));
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 8; ++v) acc[v] = warp_sum(acc[v]);
+  if (lane == 0) {
+    if (pos) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = sel[k];
+        float val = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) val = (u == v) ? acc[u] : val;
+        out[item * 4 + k] = val;
+      }
+    } else {
+      float4* o = reinterpret_cast<float4*>(out + item * 8);
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+}
+
+// ---- hidden_states[-1] tap (reference train_XGBoost.py:104-105, notebooks/examples.ipynb:183) ----
+// out[b, t, j]     = HF[b, t, j]                 j <  d
+// out[b, t, d + j] = HR[b, L-1-t, d-1-j]         (RC half: sequence and channel reversed back)
+template <typename T>
+__global__ void hidden_tap_kernel(const T* __restrict__ H, T* __restrict__ out, int B, int L, int d) {
+  const int vec_per_row = (2 * d) / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * L * vec_per_row;
+  if (gid >= total) return;
+  const int v = static_cast<int>(gid % vec_per_row);
+  const long long bt = gid / vec_per_row;
+  const int t = static_cast<int>(bt % L);
+  const int b = static_cast<int>(bt / L);
+  const int j0 = v * 8;
+  float x[8];
+  if (j0 < d) {
+    load8<T>(H + (static_cast<long long>(b) * L + t) * d + j0, x);
+  } else {
+    const int jj = j0 - d;  // out channels d+jj .. d+jj+7  <-  HR channels d-1-jj .. d-8-jj
+    float y[8];
+    load8<T>(H + (static_cast<long long>(B + b) * L + (L - 1 - t)) * d + (d - 8 - jj), y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = y[7 - i];
+  }
+  store8<T>(out + bt * (2 * d) + j0, x);
+}
+
+}  // namespace pcad

@@ -1,0 +1,831 @@
+// libpcad: C ABI (include/pcad.h) over the sm_100a kernels.  Handle = weights + workspace + launch plan.
+#include "../../include/pcad.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tcgen05.cuh"
+#include "scan.cuh"
+
+using namespace pcad;
+
+namespace {
+
+char g_create_error[512] = "";
+
+struct DirWeights {
+  float* conv_w = nullptr;   // [E, 4]
+  float* conv_b = nullptr;   // [E]
+  void* x_proj = nullptr;    // [RP, E] act dtype, rows >= R+2N zero
+  void* dt_proj = nullptr;   // [E, R] act dtype
+  float* dt_bias = nullptr;  // [E]
+  float* A = nullptr;        // [E, N] = -exp(A_log)
+  float* D = nullptr;        // [E]
+  bool has[7] = {false, false, false, false, false, false, false};
+};
+
+struct LayerWeights {
+  void* in_proj = nullptr;   // [2E, d] act dtype
+  void* out_proj = nullptr;  // [d, E] act dtype
+  float* norm_w = nullptr;   // [d]
+  DirWeights dir[2];
+  bool has_in = false, has_out = false, has_norm = false;
+};
+
+struct Workspace {
+  int B = 0, L = 0;
+  size_t bytes = 0;
+  uint8_t* base = nullptr;
+  uint8_t* ids = nullptr;      // [B, L] u8
+  void* hid = nullptr;         // [T, d]
+  void* resid = nullptr;       // [T, d] (RT)
+  void* normed = nullptr;      // [T, d]
+  void* xz = nullptr;          // [T, 2E]
+  void* xc[2] = {nullptr, nullptr};     // [T, E]
+  void* dbc[2] = {nullptr, nullptr};    // [T, RP]
+  void* delta[2] = {nullptr, nullptr};  // [T, E]
+  void* y = nullptr;           // [T, E]
+  uint8_t* ascii = nullptr;    // [B, L] staging for the host entry
+  float* logits4 = nullptr;    // [B, 4] staging for the host entry
+  int* pos = nullptr;          // [B] staging for the host entry
+};
+
+}  // namespace
+
+struct pcad_handle {
+  pcad_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  int d = 0, E = 0, N = 16, R = 0, RP = 0, V = 8;
+  bool f32 = false;
+  size_t act_size = 2;
+  bool finalized = false;
+  char err[512] = "";
+  std::vector<LayerWeights> layers;
+  void* emb = nullptr;        // [V, d] act dtype
+  float* head_w = nullptr;    // [V, d] fp32
+  float* norm_f = nullptr;    // [d]
+  bool has_emb = false, has_head = false, has_norm_f = false;
+  uint8_t* comp_dev = nullptr;   // [V]
+  uint8_t* lut_dev = nullptr;    // [256]
+  int* sel_dev = nullptr;        // [4] acgt ids
+  int* bad_flag = nullptr;       // device flag for out-of-range ids
+  int mask_id = 1;
+  int acgt[4] = {3, 4, 5, 6};
+  Workspace ws;
+  std::vector<void*> allocs;
+  // profiling
+  bool profiling = false;
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
+  std::vector<cudaEvent_t> event_pool;
+  float prof_ms[PCAD_ST_COUNT];
+  int64_t prof_launches[PCAD_ST_COUNT];
+  int64_t launch_count = 0;
+};
+
+namespace {
+
+int fail(pcad_handle* h, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  char* dst = h ? h->err : g_create_error;
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail((h), PCAD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+int dev_alloc(pcad_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+  if (e != cudaSuccess) return fail(h, PCAD_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return PCAD_OK;
+}
+
+// ---- small conversion kernels used at weight-ingest time -------------------------------------
+template <typename SrcT, typename DstT>
+__global__ void convert_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v;
+  if constexpr (sizeof(SrcT) == 2) v = __bfloat162float(src[i]); else v = src[i];
+  if constexpr (sizeof(DstT) == 2) dst[i] = __float2bfloat16_rn(v); else dst[i] = v;
+}
+__global__ void half_to_float_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __half2float(src[i]);
+}
+__global__ void neg_exp_kernel(float* __restrict__ a, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = -expf(a[i]);
+}
+
+// Copy `n` elements of src (host or device, src_dtype) into dst (device, fp32 or bf16).
+int ingest(pcad_handle* h, const void* src, int src_dtype, void* dst, bool dst_f32, long long n) {
+  const size_t src_size = (src_dtype == PCAD_F32) ? 4 : 2;
+  void* stage = nullptr;
+  CUDA_TRY(h, cudaMalloc(&stage, n * src_size));
+  cudaError_t e = cudaMemcpy(stage, src, n * src_size, cudaMemcpyDefault);
+  if (e != cudaSuccess) { cudaFree(stage); return fail(h, PCAD_ERR_CUDA, "weight copy failed: %s", cudaGetErrorString(e)); }
+  float* f32_tmp = nullptr;
+  const void* s = stage;
+  int s_dtype = src_dtype;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((n + threads - 1) / threads);
+  if (src_dtype == PCAD_F16) {
+    e = cudaMalloc(reinterpret_cast<void**>(&f32_tmp), n * 4);
+    if (e != cudaSuccess) { cudaFree(stage); return fail(h, PCAD_ERR_NOMEM, "cudaMalloc failed"); }
+    half_to_float_kernel<<<blocks, threads>>>(static_cast<const __half*>(stage), f32_tmp, n);
+    s = f32_tmp;
+    s_dtype = PCAD_F32;
+  }
+  if (s_dtype == PCAD_F32) {
+    if (dst_f32) convert_kernel<float, float><<<blocks, threads>>>(static_cast<const float*>(s), static_cast<float*>(dst), n);
+    else convert_kernel<float, bf16><<<blocks, threads>>>(static_cast<const float*>(s), static_cast<bf16*>(dst), n);
+  } else {
+    if (dst_f32) convert_kernel<bf16, float><<<blocks, threads>>>(static_cast<const bf16*>(s), static_cast<float*>(dst), n);
+    else convert_kernel<bf16, bf16><<<blocks, threads>>>(static_cast<const bf16*>(s), static_cast<bf16*>(dst), n);
+  }
+  e = cudaDeviceSynchronize();
+  cudaFree(stage);
+  if (f32_tmp) cudaFree(f32_tmp);
+  if (e != cudaSuccess) return fail(h, PCAD_ERR_CUDA, "weight conversion failed: %s", cudaGetErrorString(e));
+  return PCAD_OK;
+}
+
+bool shape_is(const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
+  // compare after dropping size-1 dims from both (conv1d.weight is [E,1,4])
+  std::vector<int64_t> a, b;
+  for (int i = 0; i < ndim; ++i) if (shape[i] != 1) a.push_back(shape[i]);
+  for (int64_t w : want) if (w != 1) b.push_back(w);
+  return a == b;
+}
+
+// ---- profiling ----------------------------------------------------------------------------------
+struct StageTimer {
+  pcad_handle* h;
+  cudaStream_t st;
+  int stage;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageTimer(pcad_handle* h_, cudaStream_t st_, int stage_, int launches = 1) : h(h_), st(st_), stage(stage_) {
+    h->launch_count += launches;
+    if (!h->profiling) return;
+    h->prof_launches[stage] += launches;
+    auto get = [&]() {
+      cudaEvent_t ev;
+      if (!h->event_pool.empty()) { ev = h->event_pool.back(); h->event_pool.pop_back(); }
+      else cudaEventCreate(&ev);
+      return ev;
+    };
+    a = get(); b = get();
+    cudaEventRecord(a, st);
+  }
+  ~StageTimer() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    h->prof_events.push_back({stage, {a, b}});
+  }
+};
+
+// ---- operator launchers (shared by the forward pass and the pcad_op_* entry points) -------------
+int op_linear(pcad_handle* h, const void* A, const void* W, void* C, long long M, int N, int K, long long lda,
+              long long ldw, long long ldc, bool f32, int num_sms, cudaStream_t st) {
+  if (f32) {
+    CUDA_TRY(h, gemm_f32_simt(static_cast<const float*>(A), static_cast<const float*>(W), static_cast<float*>(C), M, N, K, lda, ldw, ldc, st));
+  } else {
+    const char* why = nullptr;
+    cudaError_t e = gemm_bf16_tcgen05(static_cast<const bf16*>(A), static_cast<const bf16*>(W), static_cast<bf16*>(C), M, N, K, lda, ldw, ldc, num_sms, st, &why);
+    if (e != cudaSuccess) return fail(h, why ? PCAD_ERR_INVALID : PCAD_ERR_CUDA, "%s", why ? why : cudaGetErrorString(e));
+  }
+  return PCAD_OK;
+}
+
+template <typename T, typename RT>
+int launch_norm_t(pcad_handle* h, const void* x, const void* res_in, const float* w, void* y, void* res_out,
+                  long long rows, int d, float eps, cudaStream_t st) {
+  const int nvec = d / 8;
+  const int ch = (nvec + 31) / 32;
+  const int warps = 8;
+  const unsigned blocks = static_cast<unsigned>((rows + warps - 1) / warps);
+#define NORM_CASE(CHV)                                                                                          \
+  add_rmsnorm_kernel<T, RT, CHV><<<blocks, warps * 32, 0, st>>>(static_cast<const T*>(x), static_cast<const RT*>(res_in), w, \
+                                                               static_cast<T*>(y), static_cast<RT*>(res_out), rows, d, eps)
+  if (ch <= 1) NORM_CASE(1);
+  else if (ch <= 2) NORM_CASE(2);
+  else if (ch <= 4) NORM_CASE(4);
+  else if (ch <= 8) NORM_CASE(8);
+  else return fail(h, PCAD_ERR_INVALID, "add_rmsnorm: d=%d too large (max 2048)", d);
+#undef NORM_CASE
+  CUDA_TRY(h, cudaGetLastError());
+  return PCAD_OK;
+}
+
+int op_add_rmsnorm(pcad_handle* h, const void* x, const void* res_in, const float* w, void* y, void* res_out,
+                   long long rows, int d, float eps, bool f32, bool res_f32, cudaStream_t st) {
+  if (d % 8) return fail(h, PCAD_ERR_INVALID, "add_rmsnorm: d must be a multiple of 8");
+  if (rows <= 0) return PCAD_OK;
+  if (f32) return launch_norm_t<float, float>(h, x, res_in, w, y, res_out, rows, d, eps, st);
+  if (res_f32) return launch_norm_t<bf16, float>(h, x, res_in, w, y, res_out, rows, d, eps, st);
+  return launch_norm_t<bf16, bf16>(h, x, res_in, w, y, res_out, rows, d, eps, st);
+}
+
+int op_conv(pcad_handle* h, const void* x, long long ldx, const float* w_f, const float* b_f, const float* w_r,
+            const float* b_r, void* out_f, void* out_r, int S, int L, int E, bool f32, cudaStream_t st) {
+  if (E % 4) return fail(h, PCAD_ERR_INVALID, "conv: E must be a multiple of 4");
+  if (S <= 0 || L <= 0) return PCAD_OK;
+  dim3 grid((E / 4 + 127) / 128, (L + kConvTT - 1) / kConvTT, S);
+  if (f32) conv_silu_kernel<float, true><<<grid, 128, 0, st>>>(static_cast<const float*>(x), ldx, w_f, b_f, w_r, b_r, static_cast<float*>(out_f), static_cast<float*>(out_r), L, E);
+  else conv_silu_kernel<bf16, false><<<grid, 128, 0, st>>>(static_cast<const bf16*>(x), ldx, w_f, b_f, w_r, b_r, static_cast<bf16*>(out_f), static_cast<bf16*>(out_r), L, E);
+  CUDA_TRY(h, cudaGetLastError());
+  return PCAD_OK;
+}
+
+int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* bc_f, const void* u_r,
+              const void* delta_r, const void* bc_r, long long ldbc, int bc_off, const void* z, long long ldz,
+              const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
+              const float* bias_r, void* y, int S, int L, int E, bool f32, cudaStream_t st) {
+  const int vec = f32 ? 4 : 8;
+  if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
+    return fail(h, PCAD_ERR_INVALID, "biscan: E, ldbc, bc_off, ldz must be multiples of %d elements", vec);
+  if (S <= 0 || L <= 0) return PCAD_OK;
+  if (S > 65535) return fail(h, PCAD_ERR_INVALID, "biscan: at most 65535 sequences per call");
+  cudaError_t e;
+  if (f32)
+    e = launch_biscan<float, true>(static_cast<const float*>(u_f), static_cast<const float*>(delta_f), static_cast<const float*>(bc_f),
+                                   static_cast<const float*>(u_r), static_cast<const float*>(delta_r), static_cast<const float*>(bc_r),
+                                   ldbc, bc_off, static_cast<const float*>(z), ldz, A_f, D_f, bias_f, A_r, D_r, bias_r,
+                                   static_cast<float*>(y), S, L, E, st);
+  else
+    e = launch_biscan<bf16, false>(static_cast<const bf16*>(u_f), static_cast<const bf16*>(delta_f), static_cast<const bf16*>(bc_f),
+                                   static_cast<const bf16*>(u_r), static_cast<const bf16*>(delta_r), static_cast<const bf16*>(bc_r),
+                                   ldbc, bc_off, static_cast<const bf16*>(z), ldz, A_f, D_f, bias_f, A_r, D_r, bias_r,
+                                   static_cast<bf16*>(y), S, L, E, st);
+  CUDA_TRY(h, e);
+  return PCAD_OK;
+}
+
+// ---- workspace ------------------------------------------------------------------------------------
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
+  const size_t T = 2ull * B * L;
+  const size_t a = h->act_size;
+  const size_t rs = h->f32 ? 4 : (h->cfg.residual_in_fp32 ? 4 : 2);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  const size_t o_ids = take(static_cast<size_t>(B) * L);
+  const size_t o_hid = take(T * h->d * a);
+  const size_t o_res = take(T * h->d * rs);
+  const size_t o_nrm = take(T * h->d * a);
+  const size_t o_xz = take(T * 2 * h->E * a);
+  const size_t o_xc0 = take(T * h->E * a), o_xc1 = take(T * h->E * a);
+  const size_t o_dbc0 = take(T * h->RP * a), o_dbc1 = take(T * h->RP * a);
+  const size_t o_dl0 = take(T * h->E * a), o_dl1 = take(T * h->E * a);
+  const size_t o_y = take(T * h->E * a);
+  const size_t o_ascii = take(static_cast<size_t>(B) * L);
+  const size_t o_l4 = take(static_cast<size_t>(B) * 4 * sizeof(float));
+  const size_t o_pos = take(static_cast<size_t>(B) * sizeof(int));
+  if (ws && ws->base) {
+    uint8_t* p = ws->base;
+    ws->ids = p + o_ids; ws->hid = p + o_hid; ws->resid = p + o_res; ws->normed = p + o_nrm; ws->xz = p + o_xz;
+    ws->xc[0] = p + o_xc0; ws->xc[1] = p + o_xc1; ws->dbc[0] = p + o_dbc0; ws->dbc[1] = p + o_dbc1;
+    ws->delta[0] = p + o_dl0; ws->delta[1] = p + o_dl1; ws->y = p + o_y;
+    ws->ascii = p + o_ascii; ws->logits4 = reinterpret_cast<float*>(p + o_l4); ws->pos = reinterpret_cast<int*>(p + o_pos);
+  }
+  return off;
+}
+
+int ensure_workspace(pcad_handle* h, int B, int L) {
+  Workspace& ws = h->ws;
+  const size_t need = workspace_layout(h, B, L, nullptr);
+  if (ws.base == nullptr || need > ws.bytes) {
+    if (ws.base) { cudaDeviceSynchronize(); cudaFree(ws.base); ws.base = nullptr; ws.bytes = 0; }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) return fail(h, PCAD_ERR_NOMEM, "workspace cudaMalloc(%zu bytes) for B=%d L=%d failed: %s", need, B, L, cudaGetErrorString(e));
+    ws.base = static_cast<uint8_t*>(p);
+    ws.bytes = need;
+  }
+  ws.B = B; ws.L = L;
+  workspace_layout(h, B, L, &ws);
+  return PCAD_OK;
+}
+
+// ---- the forward pass over the strand-major layout --------------------------------------------------
+// ids (u8 [B, L]) are already in ws.ids.  Leaves the final normed hidden state in ws.normed.
+int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
+  Workspace& ws = h->ws;
+  const long long T = 2LL * B * L;
+  const int S = 2 * B;
+  const int d = h->d, E = h->E, R = h->R, RP = h->RP;
+  const bool f32 = h->f32;
+  const bool res_f32 = f32 || h->cfg.residual_in_fp32;
+  {
+    StageTimer tm(h, st, PCAD_ST_EMBED);
+    const long long total = T * (d / 8);
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    if (f32) embed_kernel<float><<<blocks, 256, 0, st>>>(ws.ids, static_cast<const float*>(h->emb), static_cast<float*>(ws.hid), B, L, d, h->comp_dev);
+    else embed_kernel<bf16><<<blocks, 256, 0, st>>>(ws.ids, static_cast<const bf16*>(h->emb), static_cast<bf16*>(ws.hid), B, L, d, h->comp_dev);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  for (int li = 0; li < h->cfg.n_layer; ++li) {
+    LayerWeights& lw = h->layers[li];
+    int rc;
+    {
+      StageTimer tm(h, st, PCAD_ST_NORM);
+      rc = op_add_rmsnorm(h, ws.hid, li == 0 ? nullptr : ws.resid, lw.norm_w, ws.normed, ws.resid, T, d, h->cfg.norm_eps, f32, res_f32, st);
+      if (rc) return rc;
+    }
+    {
+      StageTimer tm(h, st, PCAD_ST_IN_PROJ);
+      rc = op_linear(h, ws.normed, lw.in_proj, ws.xz, T, 2 * E, d, d, d, 2 * E, f32, h->num_sms, st);
+      if (rc) return rc;
+    }
+    {
+      StageTimer tm(h, st, PCAD_ST_CONV);
+      rc = op_conv(h, ws.xz, 2 * E, lw.dir[0].conv_w, lw.dir[0].conv_b, lw.dir[1].conv_w, lw.dir[1].conv_b, ws.xc[0], ws.xc[1], S, L, E, f32, st);
+      if (rc) return rc;
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+      {
+        StageTimer tm(h, st, PCAD_ST_X_PROJ);
+        rc = op_linear(h, ws.xc[dir], lw.dir[dir].x_proj, ws.dbc[dir], T, RP, E, E, E, RP, f32, h->num_sms, st);
+        if (rc) return rc;
+      }
+      {
+        StageTimer tm(h, st, PCAD_ST_DT_PROJ);
+        rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, f32, h->num_sms, st);
+        if (rc) return rc;
+      }
+    }
+    {
+      StageTimer tm(h, st, PCAD_ST_SCAN);
+      const uint8_t* zbase = static_cast<const uint8_t*>(ws.xz) + static_cast<size_t>(E) * h->act_size;
+      rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
+                     lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st);
+      if (rc) return rc;
+    }
+    {
+      StageTimer tm(h, st, PCAD_ST_OUT_PROJ);
+      rc = op_linear(h, ws.y, lw.out_proj, ws.hid, T, d, E, E, E, d, f32, h->num_sms, st);
+      if (rc) return rc;
+    }
+  }
+  {
+    StageTimer tm(h, st, PCAD_ST_NORM);
+    int rc = op_add_rmsnorm(h, ws.hid, h->cfg.n_layer == 0 ? nullptr : ws.resid, h->norm_f, ws.normed, nullptr, T, d, h->cfg.norm_eps, f32, res_f32, st);
+    if (rc) return rc;
+  }
+  return PCAD_OK;
+}
+
+int run_head(pcad_handle* h, int B, int L, const int* pos_dev, int n_pos, float* out, cudaStream_t st) {
+  StageTimer tm(h, st, PCAD_ST_HEAD);
+  const long long items = pos_dev ? static_cast<long long>(B) * n_pos : static_cast<long long>(B) * L;
+  if (items <= 0) return PCAD_OK;
+  const unsigned blocks = static_cast<unsigned>((items + 7) / 8);
+  if (h->f32) lm_head_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(h->ws.normed), h->head_w, h->comp_dev, pos_dev, n_pos, h->sel_dev, out, B, L, h->d);
+  else lm_head_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(h->ws.normed), h->head_w, h->comp_dev, pos_dev, n_pos, h->sel_dev, out, B, L, h->d);
+  CUDA_TRY(h, cudaGetLastError());
+  return PCAD_OK;
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int check_call(pcad_handle* h, int B, int L) {
+  if (!h) return PCAD_ERR_INVALID;
+  if (!h->finalized) return fail(h, PCAD_ERR_STATE, "pcad_finalize must succeed before a forward call");
+  if (B < 0 || L < 0) return fail(h, PCAD_ERR_INVALID, "negative batch or length");
+  if (2LL * B > 65535) return fail(h, PCAD_ERR_INVALID, "B=%d too large for one call (max 32767)", B);
+  return PCAD_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int pcad_abi_version(void) { return PCAD_ABI_VERSION; }
+
+const char* pcad_last_error(const pcad_handle* h) { return h ? h->err : g_create_error; }
+
+int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
+  if (!cfg || !out) return fail(nullptr, PCAD_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->d_state != 16) return fail(nullptr, PCAD_ERR_INVALID, "unsupported d_state=%d (engine is specialised for 16)", cfg->d_state);
+  if (cfg->d_conv != 4) return fail(nullptr, PCAD_ERR_INVALID, "unsupported d_conv=%d (engine is specialised for 4)", cfg->d_conv);
+  if (cfg->vocab_size != 8) return fail(nullptr, PCAD_ERR_INVALID, "unsupported vocab_size=%d (LM head is specialised for 8 rows)", cfg->vocab_size);
+  if (cfg->d_model <= 0 || cfg->d_model % 128 != 0 || cfg->d_model > 2048)
+    return fail(nullptr, PCAD_ERR_INVALID, "unsupported d_model=%d (need a multiple of 128, <= 2048)", cfg->d_model);
+  if (cfg->expand != 2) return fail(nullptr, PCAD_ERR_INVALID, "unsupported expand=%d", cfg->expand);
+  if (cfg->dt_rank <= 0 || cfg->dt_rank % 8 != 0) return fail(nullptr, PCAD_ERR_INVALID, "unsupported dt_rank=%d (need a multiple of 8)", cfg->dt_rank);
+  if (cfg->n_layer < 0) return fail(nullptr, PCAD_ERR_INVALID, "negative n_layer");
+  if (cfg->dtype != PCAD_BF16 && cfg->dtype != PCAD_F32) return fail(nullptr, PCAD_ERR_INVALID, "dtype must be PCAD_BF16 or PCAD_F32");
+  for (int i = 0; i < cfg->vocab_size; ++i)
+    if (cfg->complement_map[i] < 0 || cfg->complement_map[i] >= cfg->vocab_size)
+      return fail(nullptr, PCAD_ERR_INVALID, "complement_map[%d]=%d out of range", i, cfg->complement_map[i]);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, PCAD_ERR_CUDA, "no CUDA device available (%s); libpcad has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, PCAD_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, PCAD_ERR_CUDA, "cudaSetDevice failed: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10)
+    return fail(nullptr, PCAD_ERR_CUDA, "device %d is sm_%d%d; libpcad is built for sm_100a only", device, prop.major, prop.minor);
+
+  pcad_handle* h = new pcad_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->d = cfg->d_model;
+  h->E = cfg->expand * cfg->d_model;
+  h->N = cfg->d_state;
+  h->R = cfg->dt_rank;
+  h->RP = (h->R + 2 * h->N + 15) / 16 * 16;
+  h->V = cfg->vocab_size;
+  h->f32 = cfg->dtype == PCAD_F32;
+  h->act_size = h->f32 ? 4 : 2;
+  memset(h->prof_ms, 0, sizeof(h->prof_ms));
+  memset(h->prof_launches, 0, sizeof(h->prof_launches));
+  h->layers.resize(cfg->n_layer);
+  int rc = PCAD_OK;
+  const size_t a = h->act_size;
+  auto A8 = [&](void** p, size_t bytes) { uint8_t* q; int r = dev_alloc<uint8_t>(h, &q, bytes); *p = q; return r; };
+  rc |= A8(&h->emb, static_cast<size_t>(h->V) * h->d * a);
+  rc |= dev_alloc(h, &h->head_w, static_cast<size_t>(h->V) * h->d);
+  rc |= dev_alloc(h, &h->norm_f, h->d);
+  rc |= dev_alloc(h, &h->comp_dev, 16);
+  rc |= dev_alloc(h, &h->lut_dev, 256);
+  rc |= dev_alloc(h, &h->sel_dev, 4);
+  rc |= dev_alloc(h, &h->bad_flag, 1);
+  for (auto& lw : h->layers) {
+    rc |= A8(&lw.in_proj, static_cast<size_t>(2) * h->E * h->d * a);
+    rc |= A8(&lw.out_proj, static_cast<size_t>(h->d) * h->E * a);
+    rc |= dev_alloc(h, &lw.norm_w, h->d);
+    for (int dir = 0; dir < 2; ++dir) {
+      DirWeights& dw = lw.dir[dir];
+      rc |= dev_alloc(h, &dw.conv_w, static_cast<size_t>(h->E) * 4);
+      rc |= dev_alloc(h, &dw.conv_b, h->E);
+      rc |= A8(&dw.x_proj, static_cast<size_t>(h->RP) * h->E * a);
+      rc |= A8(&dw.dt_proj, static_cast<size_t>(h->E) * h->R * a);
+      rc |= dev_alloc(h, &dw.dt_bias, h->E);
+      rc |= dev_alloc(h, &dw.A, static_cast<size_t>(h->E) * h->N);
+      rc |= dev_alloc(h, &dw.D, h->E);
+      if (rc == PCAD_OK) cudaMemset(dw.x_proj, 0, static_cast<size_t>(h->RP) * h->E * a);
+    }
+    if (rc != PCAD_OK) break;
+  }
+  if (rc != PCAD_OK) {
+    snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
+    pcad_destroy(h);
+    return PCAD_ERR_NOMEM;
+  }
+  uint8_t comp8[16] = {0};
+  for (int i = 0; i < h->V; ++i) comp8[i] = static_cast<uint8_t>(cfg->complement_map[i]);
+  cudaMemcpy(h->comp_dev, comp8, 16, cudaMemcpyHostToDevice);
+  cudaMemset(h->bad_flag, 0, sizeof(int));
+  // default tokenizer tables: [PAD]=0 [MASK]=1 [UNK]=2 a=3 c=4 g=5 t=6, case-folded, everything else UNK
+  uint8_t lut[256];
+  memset(lut, 2, sizeof(lut));
+  lut['a'] = lut['A'] = 3; lut['c'] = lut['C'] = 4; lut['g'] = lut['G'] = 5; lut['t'] = lut['T'] = 6;
+  const int32_t acgt[4] = {3, 4, 5, 6};
+  *out = h;
+  return pcad_set_tokenizer(h, lut, 1, acgt);
+}
+
+void pcad_destroy(pcad_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& pe : h->prof_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
+  for (auto ev : h->event_pool) cudaEventDestroy(ev);
+  if (h->ws.base) cudaFree(h->ws.base);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+int pcad_set_tokenizer(pcad_handle* h, const uint8_t lut[256], int mask_id, const int32_t acgt_ids[4]) {
+  if (!h || !lut || !acgt_ids) return PCAD_ERR_INVALID;
+  if (mask_id < 0 || mask_id >= h->V) return fail(h, PCAD_ERR_INVALID, "mask_id %d out of range", mask_id);
+  for (int i = 0; i < 256; ++i) if (lut[i] >= h->V) return fail(h, PCAD_ERR_INVALID, "lut[%d]=%d out of range", i, lut[i]);
+  for (int k = 0; k < 4; ++k) if (acgt_ids[k] < 0 || acgt_ids[k] >= h->V) return fail(h, PCAD_ERR_INVALID, "acgt id out of range");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemcpy(h->lut_dev, lut, 256, cudaMemcpyHostToDevice));
+  int sel[4] = {acgt_ids[0], acgt_ids[1], acgt_ids[2], acgt_ids[3]};
+  CUDA_TRY(h, cudaMemcpy(h->sel_dev, sel, sizeof(sel), cudaMemcpyHostToDevice));
+  h->mask_id = mask_id;
+  for (int k = 0; k < 4; ++k) h->acgt[k] = acgt_ids[k];
+  return PCAD_OK;
+}
+
+int pcad_set_weight(pcad_handle* h, const char* name, const void* data, const int64_t* shape, int ndim, int src_dtype) {
+  if (!h || !name || !data || !shape) return PCAD_ERR_INVALID;
+  if (src_dtype != PCAD_BF16 && src_dtype != PCAD_F32 && src_dtype != PCAD_F16) return fail(h, PCAD_ERR_INVALID, "bad src_dtype for %s", name);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  h->finalized = false;
+  const int d = h->d, E = h->E, N = h->N, R = h->R, V = h->V;
+  const std::string s(name);
+  auto bad_shape = [&]() { return fail(h, PCAD_ERR_INVALID, "unexpected shape for %s", name); };
+  if (s == "caduceus.backbone.embeddings.word_embeddings.embedding.weight") {
+    if (!shape_is(shape, ndim, {V, d})) return bad_shape();
+    int rc = ingest(h, data, src_dtype, h->emb, h->f32, static_cast<long long>(V) * d);
+    h->has_emb = rc == PCAD_OK;
+    return rc;
+  }
+  if (s == "lm_head.lm_head.weight") {
+    if (!shape_is(shape, ndim, {V, d})) return bad_shape();
+    int rc = ingest(h, data, src_dtype, h->head_w, true, static_cast<long long>(V) * d);
+    h->has_head = rc == PCAD_OK;
+    return rc;
+  }
+  if (s == "caduceus.backbone.norm_f.weight") {
+    if (!shape_is(shape, ndim, {d})) return bad_shape();
+    int rc = ingest(h, data, src_dtype, h->norm_f, true, d);
+    h->has_norm_f = rc == PCAD_OK;
+    return rc;
+  }
+  const std::string lp = "caduceus.backbone.layers.";
+  if (s.compare(0, lp.size(), lp) != 0) return fail(h, PCAD_ERR_INVALID, "unknown weight name %s", name);
+  size_t dot = s.find('.', lp.size());
+  if (dot == std::string::npos) return fail(h, PCAD_ERR_INVALID, "unknown weight name %s", name);
+  const int li = atoi(s.substr(lp.size(), dot - lp.size()).c_str());
+  if (li < 0 || li >= h->cfg.n_layer) return fail(h, PCAD_ERR_INVALID, "layer index out of range in %s", name);
+  LayerWeights& lw = h->layers[li];
+  const std::string rest = s.substr(dot + 1);
+  if (rest == "norm.weight") {
+    if (!shape_is(shape, ndim, {d})) return bad_shape();
+    int rc = ingest(h, data, src_dtype, lw.norm_w, true, d);
+    lw.has_norm = rc == PCAD_OK;
+    return rc;
+  }
+  const std::string mp = "mixer.submodule.mamba_";
+  if (rest.compare(0, mp.size(), mp) != 0) return fail(h, PCAD_ERR_INVALID, "unknown weight name %s", name);
+  int dir;
+  if (rest.compare(mp.size(), 4, "fwd.") == 0) dir = 0;
+  else if (rest.compare(mp.size(), 4, "rev.") == 0) dir = 1;
+  else return fail(h, PCAD_ERR_INVALID, "unknown weight name %s", name);
+  const std::string leaf = rest.substr(mp.size() + 4);
+  DirWeights& dw = lw.dir[dir];
+  int rc;
+  if (leaf == "in_proj.weight") {
+    if (!shape_is(shape, ndim, {2 * E, d})) return bad_shape();
+    if (dir == 1) return PCAD_OK;  // tied to mamba_fwd (bidirectional_weight_tie)
+    rc = ingest(h, data, src_dtype, lw.in_proj, h->f32, 2LL * E * d);
+    lw.has_in = rc == PCAD_OK;
+  } else if (leaf == "out_proj.weight") {
+    if (!shape_is(shape, ndim, {d, E})) return bad_shape();
+    if (dir == 1) return PCAD_OK;
+    rc = ingest(h, data, src_dtype, lw.out_proj, h->f32, static_cast<long long>(d) * E);
+    lw.has_out = rc == PCAD_OK;
+  } else if (leaf == "conv1d.weight") {
+    if (!shape_is(shape, ndim, {E, 4})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.conv_w, true, static_cast<long long>(E) * 4);
+    dw.has[0] = rc == PCAD_OK;
+  } else if (leaf == "conv1d.bias") {
+    if (!shape_is(shape, ndim, {E})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.conv_b, true, E);
+    dw.has[1] = rc == PCAD_OK;
+  } else if (leaf == "x_proj.weight") {
+    if (!shape_is(shape, ndim, {R + 2 * N, E})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.x_proj, h->f32, static_cast<long long>(R + 2 * N) * E);  // rows beyond stay zero
+    dw.has[2] = rc == PCAD_OK;
+  } else if (leaf == "dt_proj.weight") {
+    if (!shape_is(shape, ndim, {E, R})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.dt_proj, h->f32, static_cast<long long>(E) * R);
+    dw.has[3] = rc == PCAD_OK;
+  } else if (leaf == "dt_proj.bias") {
+    if (!shape_is(shape, ndim, {E})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.dt_bias, true, E);
+    dw.has[4] = rc == PCAD_OK;
+  } else if (leaf == "A_log") {
+    if (!shape_is(shape, ndim, {E, N})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.A, true, static_cast<long long>(E) * N);
+    if (rc == PCAD_OK) {
+      const long long n = static_cast<long long>(E) * N;
+      neg_exp_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(dw.A, n);  // A = -exp(A_log), fp32
+      CUDA_TRY(h, cudaDeviceSynchronize());
+    }
+    dw.has[5] = rc == PCAD_OK;
+  } else if (leaf == "D") {
+    if (!shape_is(shape, ndim, {E})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.D, true, E);
+    dw.has[6] = rc == PCAD_OK;
+  } else {
+    return fail(h, PCAD_ERR_INVALID, "unknown weight name %s", name);
+  }
+  return rc;
+}
+
+int pcad_finalize(pcad_handle* h) {
+  if (!h) return PCAD_ERR_INVALID;
+  if (!h->has_emb) return fail(h, PCAD_ERR_MISSING, "missing weight: embedding");
+  if (!h->has_norm_f) return fail(h, PCAD_ERR_MISSING, "missing weight: norm_f");
+  if (!h->has_head) {  // tied LM head: derive from the embedding
+    const long long n = static_cast<long long>(h->V) * h->d;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->f32) convert_kernel<float, float><<<static_cast<unsigned>((n + 255) / 256), 256>>>(static_cast<const float*>(h->emb), h->head_w, n);
+    else convert_kernel<bf16, float><<<static_cast<unsigned>((n + 255) / 256), 256>>>(static_cast<const bf16*>(h->emb), h->head_w, n);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->has_head = true;
+  }
+  static const char* names[7] = {"conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight", "dt_proj.bias", "A_log", "D"};
+  for (int li = 0; li < h->cfg.n_layer; ++li) {
+    const LayerWeights& lw = h->layers[li];
+    if (!lw.has_in) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d in_proj.weight", li);
+    if (!lw.has_out) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d out_proj.weight", li);
+    if (!lw.has_norm) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d norm.weight", li);
+    for (int dir = 0; dir < 2; ++dir)
+      for (int k = 0; k < 7; ++k)
+        if (!lw.dir[dir].has[k]) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d mamba_%s.%s", li, dir ? "rev" : "fwd", names[k]);
+  }
+  h->finalized = true;
+  return PCAD_OK;
+}
+
+int pcad_workspace_bytes(pcad_handle* h, int B, int L, size_t* out) {
+  if (!h || !out || B < 0 || L < 0) return PCAD_ERR_INVALID;
+  *out = workspace_layout(h, B, L, nullptr);
+  return PCAD_OK;
+}
+
+int pcad_tokenize(pcad_handle* h, const uint8_t* ascii_dev, int64_t n, uint8_t* ids_dev, void* stream) {
+  if (!h || (n > 0 && (!ascii_dev || !ids_dev))) return PCAD_ERR_INVALID;
+  if (n <= 0) return PCAD_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StageTimer tm(h, st, PCAD_ST_MISC);
+  tokenize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ascii_dev, ids_dev, n, h->lut_dev, 1, -1, 0);
+  CUDA_TRY(h, cudaGetLastError());
+  return PCAD_OK;
+}
+
+int pcad_forward(pcad_handle* h, const int64_t* ids_dev, int B, int L, float* logits_dev, void* hidden_dev, void* stream) {
+  int rc = check_call(h, B, L);
+  if (rc) return rc;
+  if (B == 0 || L == 0) return PCAD_OK;
+  if (!ids_dev) return fail(h, PCAD_ERR_INVALID, "ids_dev is null");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B, L);
+  if (rc) return rc;
+  {
+    StageTimer tm(h, st, PCAD_ST_MISC);
+    const long long n = static_cast<long long>(B) * L;
+    ids64_to_u8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long*>(ids_dev), h->ws.ids, n, h->V, h->bad_flag);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  rc = run_backbone(h, B, L, st);
+  if (rc) return rc;
+  if (logits_dev) {
+    rc = run_head(h, B, L, nullptr, 0, logits_dev, st);
+    if (rc) return rc;
+  }
+  if (hidden_dev) {
+    StageTimer tm(h, st, PCAD_ST_MISC);
+    const long long total = static_cast<long long>(B) * L * (2 * h->d / 8);
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    if (h->f32) hidden_tap_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(h->ws.normed), static_cast<float*>(hidden_dev), B, L, h->d);
+    else hidden_tap_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(h->ws.normed), static_cast<bf16*>(hidden_dev), B, L, h->d);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  return PCAD_OK;
+}
+
+int pcad_score_masked(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos_dev, int B, int L, int n_mask, float* logits4_dev, void* stream) {
+  int rc = check_call(h, B, L);
+  if (rc) return rc;
+  if (B == 0 || L == 0 || n_mask == 0) return PCAD_OK;
+  if (!ids_dev || !pos_dev || !logits4_dev || n_mask < 0) return fail(h, PCAD_ERR_INVALID, "null or negative argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B, L);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(h->ws.ids, ids_dev, static_cast<size_t>(B) * L, cudaMemcpyDeviceToDevice, st));
+  rc = run_backbone(h, B, L, st);
+  if (rc) return rc;
+  return run_head(h, B, L, pos_dev, n_mask, logits4_dev, st);
+}
+
+int pcad_score_windows_host(pcad_handle* h, const uint8_t* ascii_host, int B, int L, int token_idx, float* logits4_host, void* stream) {
+  int rc = check_call(h, B, L);
+  if (rc) return rc;
+  if (B == 0 || L == 0) return PCAD_OK;
+  if (!ascii_host || !logits4_host) return fail(h, PCAD_ERR_INVALID, "null argument");
+  if (token_idx < 0 || token_idx >= L) return fail(h, PCAD_ERR_INVALID, "token_idx %d outside [0, %d)", token_idx, L);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B, L);
+  if (rc) return rc;
+  Workspace& ws = h->ws;
+  const long long n = static_cast<long long>(B) * L;
+  CUDA_TRY(h, cudaMemcpyAsync(ws.ascii, ascii_host, n, cudaMemcpyHostToDevice, st));
+  {
+    StageTimer tm(h, st, PCAD_ST_MISC, 2);
+    tokenize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ascii, ws.ids, n, h->lut_dev, L, token_idx, h->mask_id);
+    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos, B, token_idx);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  rc = run_backbone(h, B, L, st);
+  if (rc) return rc;
+  rc = run_head(h, B, L, ws.pos, 1, ws.logits4, st);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaMemcpyAsync(logits4_host, ws.logits4, static_cast<size_t>(B) * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return PCAD_OK;
+}
+
+int pcad_set_profiling(pcad_handle* h, int enabled) {
+  if (!h) return PCAD_ERR_INVALID;
+  for (auto& pe : h->prof_events) { h->event_pool.push_back(pe.second.first); h->event_pool.push_back(pe.second.second); }
+  h->prof_events.clear();
+  memset(h->prof_ms, 0, sizeof(h->prof_ms));
+  memset(h->prof_launches, 0, sizeof(h->prof_launches));
+  h->profiling = enabled != 0;
+  return PCAD_OK;
+}
+
+int pcad_get_profile(pcad_handle* h, float ms[PCAD_ST_COUNT], int64_t launches[PCAD_ST_COUNT]) {
+  if (!h || !ms || !launches) return PCAD_ERR_INVALID;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  for (auto& pe : h->prof_events) {
+    CUDA_TRY(h, cudaEventSynchronize(pe.second.second));
+    float t = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&t, pe.second.first, pe.second.second));
+    h->prof_ms[pe.first] += t;
+    h->event_pool.push_back(pe.second.first);
+    h->event_pool.push_back(pe.second.second);
+  }
+  h->prof_events.clear();
+  for (int i = 0; i < PCAD_ST_COUNT; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_launches[i]; }
+  return PCAD_OK;
+}
+
+int64_t pcad_launch_count(const pcad_handle* h) { return h ? h->launch_count : 0; }
+
+// ---- single-operator entry points ---------------------------------------------------------------------
+static pcad_handle* op_scratch() {
+  static pcad_handle scratch;  // only .err and .launch_count are used
+  return &scratch;
+}
+static int op_fail_to_global(int rc) {
+  if (rc != PCAD_OK) snprintf(g_create_error, sizeof(g_create_error), "%s", op_scratch()->err);
+  return rc;
+}
+static int op_num_sms() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+int pcad_op_linear(const void* A, const void* W, void* C, int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, dtype == PCAD_F32, op_num_sms(), static_cast<cudaStream_t>(stream)));
+}
+
+int pcad_op_add_rmsnorm(const void* x, const void* res_in, const float* w, void* y, void* res_out, int64_t rows, int d, float eps, int dtype, int res_dtype, void* stream) {
+  if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
+  if (dtype == PCAD_F32 && res_dtype != PCAD_F32) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_add_rmsnorm(op_scratch(), x, res_in, w, y, res_out, rows, d, eps, dtype == PCAD_F32, res_dtype == PCAD_F32, static_cast<cudaStream_t>(stream)));
+}
+
+int pcad_op_conv_silu(const void* x, int64_t ldx, const float* w_f, const float* b_f, const float* w_r, const float* b_r, void* out_f, void* out_r, int S, int L, int E, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_conv(op_scratch(), x, ldx, w_f, b_f, w_r, b_r, out_f, out_r, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream)));
+}
+
+int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f, const void* u_r, const void* delta_r, const void* bc_r,
+                   int64_t ldbc, int bc_off, const void* z, int64_t ldz, const float* A_f, const float* D_f, const float* dt_bias_f,
+                   const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_biscan(op_scratch(), u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
+                                     A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream)));
+}
+
+}  // extern "C"

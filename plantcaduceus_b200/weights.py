@@ -1,0 +1,104 @@
+"""State-dict naming and seeded random initialisation for Caduceus weights.
+
+Names are the ones the HF-hub checkpoint carries (module tree printed at reference
+notebooks/examples.ipynb:61-98; Mamba parameter names corroborated by the LoRA targets at
+reference src/lora_fine_tune.py:609-617):
+
+    caduceus.backbone.embeddings.word_embeddings.embedding.weight            [V, d]
+    caduceus.backbone.layers.{i}.mixer.submodule.mamba_{fwd,rev}.in_proj.weight   [2E, d]   (rev aliases fwd)
+    ...                                                   .conv1d.weight     [E, 1, 4]
+    ...                                                   .conv1d.bias       [E]
+    ...                                                   .x_proj.weight     [R+2N, E]
+    ...                                                   .dt_proj.weight    [E, R]
+    ...                                                   .dt_proj.bias      [E]
+    ...                                                   .A_log             [E, N]
+    ...                                                   .D                 [E]
+    ...                                                   .out_proj.weight   [d, E]   (rev aliases fwd)
+    caduceus.backbone.layers.{i}.norm.weight                                 [d]
+    caduceus.backbone.norm_f.weight                                          [d]
+    lm_head.lm_head.weight                                                   [V, d]   (tied to the embedding)
+
+There is no network in the build/bench environment, so benchmarks and parity tests run on
+random-initialised weights of the published architecture (BASELINE.json configs 1-2).  The
+initialisation below follows the Mamba-1 recipe in spirit (S4D-real A with jitter so that the
+A[e,n] = -(n+1) structure cannot be exploited by a kernel, inverse-softplus dt bias drawn
+log-uniformly in [1e-3, 1e-1]) and is fully determined by ``seed`` through a CPU generator.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+from .configuration import CaduceusConfig
+
+PREFIX = "caduceus.backbone."
+EMB_KEY = PREFIX + "embeddings.word_embeddings.embedding.weight"
+HEAD_KEY = "lm_head.lm_head.weight"
+NORM_F_KEY = PREFIX + "norm_f.weight"
+DIRS = ("mamba_fwd", "mamba_rev")
+PER_DIR = ("conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight", "dt_proj.bias", "A_log", "D")
+SHARED = ("in_proj.weight", "out_proj.weight")
+
+
+def layer_key(i: int, direction: str, name: str) -> str:
+    return f"{PREFIX}layers.{i}.mixer.submodule.{direction}.{name}"
+
+
+def norm_key(i: int) -> str:
+    return f"{PREFIX}layers.{i}.norm.weight"
+
+
+def random_init_state_dict(cfg: CaduceusConfig, seed: int = 0,
+                           dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+    """Seeded random weights with the checkpoint's names, shapes and tying."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    d, E, N, R, K, V = cfg.d_model, cfg.d_inner, cfg.d_state, cfg.dt_rank, cfg.d_conv, cfg.vocab_size
+
+    def uniform(shape, bound):
+        return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+
+    def normal(shape, std):
+        return torch.randn(shape, generator=g, dtype=torch.float32) * std
+
+    sd: Dict[str, torch.Tensor] = {}
+    emb = normal((V, d), 0.02)
+    sd[EMB_KEY] = emb
+    sd[HEAD_KEY] = emb  # tied (225.36 M parameter count)
+    for i in range(cfg.n_layer):
+        w_in = uniform((2 * E, d), 1.0 / math.sqrt(d))
+        w_out = uniform((d, E), 1.0 / math.sqrt(E)) / math.sqrt(2.0 * cfg.n_layer)
+        for direction in DIRS:
+            sd[layer_key(i, direction, "in_proj.weight")] = w_in
+            sd[layer_key(i, direction, "out_proj.weight")] = w_out
+            sd[layer_key(i, direction, "conv1d.weight")] = uniform((E, 1, K), 1.0 / math.sqrt(K))
+            sd[layer_key(i, direction, "conv1d.bias")] = uniform((E,), 1.0 / math.sqrt(K))
+            sd[layer_key(i, direction, "x_proj.weight")] = uniform((R + 2 * N, E), 1.0 / math.sqrt(E))
+            sd[layer_key(i, direction, "dt_proj.weight")] = uniform((E, R), R ** -0.5)
+            dt = torch.exp(torch.rand((E,), generator=g) * (math.log(0.1) - math.log(1e-3)) + math.log(1e-3))
+            dt = dt.clamp(min=1e-4)
+            sd[layer_key(i, direction, "dt_proj.bias")] = dt + torch.log(-torch.expm1(-dt))
+            a = torch.arange(1, N + 1, dtype=torch.float32).repeat(E, 1)
+            sd[layer_key(i, direction, "A_log")] = torch.log(a) + normal((E, N), 0.1)
+            sd[layer_key(i, direction, "D")] = 1.0 + normal((E,), 0.1)
+        sd[norm_key(i)] = 1.0 + normal((d,), 0.1)
+    sd[NORM_F_KEY] = 1.0 + normal((d,), 0.1)
+    if dtype != torch.float32:
+        # from_pretrained(torch_dtype=...) casts every floating parameter, A_log and D included.
+        cast = {k: v.to(dtype) for k, v in sd.items()}
+        cast[HEAD_KEY] = cast[EMB_KEY]
+        sd = cast
+    return sd
+
+
+def count_parameters(sd: Dict[str, torch.Tensor]) -> int:
+    """Unique parameter count (tied tensors counted once), for the README.md:60-63 check."""
+    seen, total = set(), 0
+    for v in sd.values():
+        p = v.data_ptr()
+        if p in seen:
+            continue
+        seen.add(p)
+        total += v.numel()
+    return total

@@ -1,0 +1,170 @@
+"""End-to-end parity of the B200 engine (through the drop-in HF-style object -> C ABI) against the CPU oracle.
+
+Tolerances are BASELINE.json's: fp32 logits within 1e-4 relative; bf16 logits within 2e-2 absolute;
+ref/alt LLR Spearman >= 0.999; tokenisation / RC indexing bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import caduceus_oracle as O
+from plantcaduceus_b200 import CaduceusConfig, CharDNATokenizer, preset, random_init_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ids(B, L, seed, mask_at=None):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(3, 7, (B, L), generator=g)
+    if mask_at is not None:
+        ids[:, mask_at] = 1
+    if L > 3:
+        ids[0, 1] = 2   # an N
+    return ids
+
+
+def rel_err(got, want):
+    return ((got - want).abs().max() / want.abs().max()).item()
+
+
+def spearman(a, b):
+    ra = np.argsort(np.argsort(a)).astype(np.float64)
+    rb = np.argsort(np.argsort(b)).astype(np.float64)
+    return float(np.corrcoef(ra, rb)[0, 1])
+
+
+@pytest.fixture(scope="module")
+def Model(cuda_device):
+    from plantcaduceus_b200.modeling import CaduceusForMaskedLM
+    return CaduceusForMaskedLM
+
+
+SMALL = [dict(d_model=128, n_layer=2), dict(d_model=256, n_layer=3, residual_in_fp32=True)]
+
+
+@pytest.mark.parametrize("kw", SMALL)
+@pytest.mark.parametrize("B,L", [(3, 64), (1, 37), (2, 512), (1, 1)])
+def test_fp32_logits_and_hidden_match_oracle(Model, cuda_device, kw, B, L):
+    cfg = CaduceusConfig(**kw)
+    sd = random_init_state_dict(cfg, seed=1)
+    ids = make_ids(B, L, seed=B * 1000 + L, mask_at=L // 2)
+    want_logits, want_hs = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32, output_hidden_states=True)
+    model = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.float32).to(cuda_device)
+    out = model(input_ids=ids.to(cuda_device), output_hidden_states=True)
+    assert out.logits.dtype == torch.float32 and out.logits.shape == (B, L, 8)
+    assert out.hidden_states[-1].shape == (B, L, 2 * cfg.d_model)
+    assert rel_err(out.logits.cpu(), want_logits) <= 1e-4
+    assert rel_err(out.hidden_states[-1].cpu(), want_hs[-1]) <= 1e-4
+
+
+@pytest.mark.parametrize("kw", SMALL)
+def test_bf16_logits_match_oracle(Model, cuda_device, kw):
+    cfg = CaduceusConfig(**kw)
+    sd = random_init_state_dict(cfg, seed=2)
+    ids = make_ids(4, 128, seed=9, mask_at=64)
+    want, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    want_bf16, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.bfloat16)
+    model = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    got = model(input_ids=ids.to(cuda_device)).logits.cpu()
+    err_fp32 = (got - want).abs().max().item()
+    err_bf16 = (got - want_bf16).abs().max().item()
+    ref_self = (want_bf16 - want).abs().max().item()
+    print(f"bf16 engine vs fp32 oracle {err_fp32:.4g}; vs bf16 oracle {err_bf16:.4g}; bf16 oracle vs fp32 oracle {ref_self:.4g}")
+    assert err_fp32 <= 2e-2
+
+
+def test_l20_fp32_and_bf16_real_shape(Model, cuda_device):
+    """BASELINE.json config 1 shape: PlantCaduceus_l20 (d 384, 20 layers), 512-bp windows, masked at 255."""
+    cfg = preset("PlantCaduceus_l20")
+    sd = random_init_state_dict(cfg, seed=0)
+    ids = make_ids(2, 512, seed=4, mask_at=255)
+    want, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    m32 = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.float32).to(cuda_device)
+    got32 = m32(input_ids=ids.to(cuda_device)).logits.cpu()
+    assert rel_err(got32, want) <= 1e-4
+    del m32
+    m16 = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    got16 = m16(input_ids=ids.to(cuda_device)).logits.cpu()
+    assert (got16 - want).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_engine_rc_equivariance(Model, cuda_device, dtype):
+    """Size-independent property: logits(RC(ids)) == logits(ids).flip(L)[..., comp]."""
+    cfg = CaduceusConfig(d_model=256, n_layer=4)
+    sd = random_init_state_dict(cfg, seed=3)
+    ids = make_ids(3, 96, seed=5, mask_at=40)
+    comp = torch.tensor([cfg.complement_map[i] for i in range(8)])
+    model = Model.from_pretrained(sd, config=cfg, torch_dtype=dtype).to(cuda_device)
+    a = model(input_ids=ids.to(cuda_device), output_hidden_states=True)
+    b = model(input_ids=O.reverse_complement_ids(ids, cfg).to(cuda_device), output_hidden_states=True)
+    # both strands run the same kernels on the same numbers, so equivariance is exact up to the order of
+    # the two-term sum in the head (commutative) -- require tight agreement
+    tol = 1e-5 if dtype == torch.float32 else 1e-5
+    assert (b.logits.cpu() - a.logits.cpu().flip(1)[..., comp]).abs().max().item() <= tol
+    assert torch.equal(b.hidden_states[-1].cpu(), a.hidden_states[-1].cpu().flip(1, 2))
+
+
+def test_score_paths_agree_and_llr_spearman(Model, cuda_device):
+    cfg = CaduceusConfig(d_model=256, n_layer=4)
+    sd = random_init_state_dict(cfg, seed=6)
+    tok = CharDNATokenizer()
+    rng = np.random.default_rng(0)
+    B, L, idx = 48, 512, 255
+    ascii_np = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(B, L))
+    ascii_np[3, 10] = ord("N")
+    ascii_np[5, 100] = ord("a")   # lower case folds
+    seqs = [bytes(r).decode() for r in ascii_np]
+    # reference-style host path (zero_shot_score.py:49-62): per-sequence encode_plus + mask
+    ids = torch.cat([tok.encode_plus(s, return_tensors="pt")["input_ids"] for s in seqs])
+    ids[:, idx] = tok.mask_token_id
+    want, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    acgt = [tok.get_vocab()[c] for c in "acgt"]
+    want4 = want[:, idx, acgt]
+
+    model = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    full = model(input_ids=ids.to(cuda_device)).logits[:, idx, acgt].cpu()
+    masked = model.score_masked(ids.to(torch.uint8).to(cuda_device), torch.full((B, 1), idx, dtype=torch.int32)).cpu()[:, 0]
+    host = model.score_windows_host(torch.from_numpy(ascii_np).pin_memory(), idx).clone()
+    assert torch.equal(full, masked)
+    assert torch.equal(full, host)
+    assert (full - want4).abs().max().item() <= 2e-2
+    # LLR for every (ref, alt) pair with ref = the window's own base
+    refs = ["ACGT".index(chr(c).upper()) for c in ascii_np[:, idx]]
+    llr_got, llr_want = [], []
+    for i, r in enumerate(refs):
+        for a in range(4):
+            if a != r:
+                llr_got.append(float(full[i, a] - full[i, r]))
+                llr_want.append(float(want4[i, a] - want4[i, r]))
+    assert spearman(np.array(llr_got), np.array(llr_want)) >= 0.999
+    # multi-mask gather (zero-shot-eval.py:129-140)
+    pos = torch.tensor([[0, 255, 511]] * B, dtype=torch.int32)
+    multi = model.score_masked(ids.to(torch.uint8).to(cuda_device), pos).cpu()
+    full_all = model(input_ids=ids.to(cuda_device)).logits.cpu()
+    assert torch.equal(multi, full_all[:, [0, 255, 511]][:, :, acgt])
+
+
+def test_device_tokenizer_bit_exact(Model, cuda_device):
+    cfg = CaduceusConfig(d_model=128, n_layer=1)
+    model = Model.from_random(cfg, seed=0).to(cuda_device)
+    tok = CharDNATokenizer()
+    all_bytes = torch.arange(256, dtype=torch.uint8).repeat(5)
+    got = model.tokenize_device(all_bytes.to(cuda_device)).cpu().numpy()
+    assert np.array_equal(got, tok.encode_bytes(all_bytes.numpy()))
+
+
+def test_errors_are_reported_not_fatal(Model, cuda_device):
+    from plantcaduceus_b200._lib import PcadError
+    with pytest.raises(ValueError):
+        Model.from_random(CaduceusConfig(d_model=128, n_layer=1, rcps=False))
+    cfg = CaduceusConfig(d_model=128, n_layer=1)
+    sd = random_init_state_dict(cfg, seed=0)
+    sd2 = {k: v for k, v in sd.items() if "layers.0.norm" not in k}
+    with pytest.raises(PcadError, match="missing weight"):
+        Model.from_pretrained(sd2, config=cfg).to(cuda_device)
+    m = Model.from_pretrained(sd, config=cfg)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(input_ids=torch.zeros(1, 8, dtype=torch.long))
+    m.to(cuda_device)
+    out = m(input_ids=torch.zeros(0, 8, dtype=torch.long, device=cuda_device))
+    assert out.logits.shape == (0, 8, 8)

@@ -1,0 +1,118 @@
+"""Pins for the CPU oracle (oracle/caduceus_oracle.py) that do not need the reference's un-vendored
+dependencies: RC equivariance, an independent Mamba-1 mixer, parameter counts, shapes."""
+import math
+
+import pytest
+import torch
+
+from oracle import caduceus_oracle as O
+from plantcaduceus_b200 import CaduceusConfig, count_parameters, preset, random_init_state_dict
+
+torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+
+
+def small_cfg(**kw):
+    base = dict(d_model=128, n_layer=2)
+    base.update(kw)
+    return CaduceusConfig(**base)
+
+
+def rand_ids(B, L, seed=0, with_special=True):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(3, 7, (B, L), generator=g)
+    if with_special:
+        ids[:, L // 2] = 1          # [MASK]
+        ids[0, 0] = 2               # [UNK] (an N in the window)
+    return ids
+
+
+@pytest.mark.parametrize("residual_in_fp32", [False, True])
+def test_rc_equivariance_exact(residual_in_fp32):
+    cfg = small_cfg(residual_in_fp32=residual_in_fp32)
+    sd = random_init_state_dict(cfg, seed=3)
+    ids = rand_ids(2, 48, seed=1)
+    logits, hs = O.caduceus_forward(sd, cfg, ids, output_hidden_states=True)
+    rc_ids = O.reverse_complement_ids(ids, cfg)
+    logits_rc, hs_rc = O.caduceus_forward(sd, cfg, rc_ids, output_hidden_states=True)
+    comp = torch.tensor([cfg.complement_map[i] for i in range(cfg.vocab_size)])
+    # SURVEY.md 8c property (1)
+    assert torch.allclose(logits_rc, logits.flip(1)[..., comp], atol=1e-5, rtol=1e-5)
+    assert torch.allclose(hs_rc[-1], hs[-1].flip(1, 2), atol=1e-5, rtol=1e-5)
+    assert logits.shape == (2, 48, 8) and logits.dtype == torch.float32
+    assert hs[-1].shape == (2, 48, 2 * cfg.d_model)
+
+
+def test_mixer_matches_transformers_mamba():
+    """Independent second opinion: transformers' MambaMixer.slow_forward (same parameter names)."""
+    from transformers import MambaConfig
+    from transformers.models.mamba.modeling_mamba import MambaMixer
+    cfg = small_cfg()
+    sd = random_init_state_dict(cfg, seed=5)
+    p = O._dir_params(sd, 0, "mamba_fwd", torch.float32)
+    mc = MambaConfig(hidden_size=cfg.d_model, state_size=16, conv_kernel=4, expand=2, time_step_rank=cfg.dt_rank,
+                     use_bias=False, use_conv_bias=True, hidden_act="silu", num_hidden_layers=1, vocab_size=8)
+    mixer = MambaMixer(mc, layer_idx=0).eval()
+    with torch.no_grad():
+        mixer.in_proj.weight.copy_(p["in_proj.weight"])
+        mixer.conv1d.weight.copy_(p["conv1d.weight"])
+        mixer.conv1d.bias.copy_(p["conv1d.bias"])
+        mixer.x_proj.weight.copy_(p["x_proj.weight"])
+        mixer.dt_proj.weight.copy_(p["dt_proj.weight"])
+        mixer.dt_proj.bias.copy_(p["dt_proj.bias"])
+        mixer.A_log.copy_(p["A_log"])
+        mixer.D.copy_(p["D"])
+        mixer.out_proj.weight.copy_(p["out_proj.weight"])
+        u = torch.randn(2, 40, cfg.d_model, generator=torch.Generator().manual_seed(0))
+        want = mixer.slow_forward(u)
+        got = O.mamba_mixer(u, p)
+    assert torch.allclose(got, want, atol=2e-5, rtol=1e-4), (got - want).abs().max()
+
+
+def test_direction_shared_projections_identity():
+    """SURVEY.md 8c property (3): Bi(u) == (y_f + flip(y_r)) W_out^T with one in_proj."""
+    cfg = small_cfg()
+    sd = random_init_state_dict(cfg, seed=7)
+    pf = O._dir_params(sd, 1, "mamba_fwd", torch.float32)
+    pr = O._dir_params(sd, 1, "mamba_rev", torch.float32)
+    assert torch.equal(pf["in_proj.weight"], pr["in_proj.weight"])
+    assert torch.equal(pf["out_proj.weight"], pr["out_proj.weight"])
+    assert not torch.equal(pf["x_proj.weight"], pr["x_proj.weight"])
+
+
+@pytest.mark.parametrize("name,millions", [("PlantCaduceus_l20", 20.87), ("PlantCaduceus_l24", 43.6),
+                                           ("PlantCaduceus_l32", 225.36)])
+def test_parameter_counts(name, millions):
+    """reference README.md:60-63 (20M / 40M / 225M); exact figures SURVEY.md Appendix A."""
+    cfg = preset(name)
+    n = 0
+    d, E, N, R, V = cfg.d_model, cfg.d_inner, cfg.d_state, cfg.dt_rank, cfg.vocab_size
+    per_dir = E * 4 + E + (R + 2 * N) * E + E * R + E + E * N + E
+    n = V * d + cfg.n_layer * (2 * E * d + d * E + 2 * per_dir + d) + d
+    assert abs(n / 1e6 - millions) < 0.05, n
+    if name == "PlantCaduceus_l20":
+        assert count_parameters(random_init_state_dict(cfg, 0)) == n
+
+
+def test_llr_equals_logit_difference():
+    """SURVEY.md 8c property (2): log(p_alt/p_ref) == logit_alt - logit_ref."""
+    cfg = small_cfg()
+    sd = random_init_state_dict(cfg, seed=11)
+    ids = rand_ids(4, 32, seed=2)
+    logits, _ = O.caduceus_forward(sd, cfg, ids)
+    probs = O.extract_acgt_probs(logits, 16, (3, 4, 5, 6))
+    refs, alts = ["A", "C", "G", "T"], ["C", "G", "T", "A"]
+    llr = O.zero_shot_llr(probs, refs, alts)
+    for i, (r, a) in enumerate(zip(refs, alts)):
+        diff = float(logits[i, 16, 3 + "ACGT".index(a)] - logits[i, 16, 3 + "ACGT".index(r)])
+        assert math.isclose(llr[i], diff, rel_tol=1e-4, abs_tol=1e-5)
+
+
+def test_bf16_mode_close_to_fp32():
+    cfg = small_cfg()
+    sd = random_init_state_dict(cfg, seed=13)
+    ids = rand_ids(2, 64, seed=3)
+    l32, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    l16, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.bfloat16)
+    assert l16.dtype == torch.float32
+    # sanity only: the reference's own bf16 logits are bf16-quantised (ulp 0.0156 at |logit| in [2,4))
+    assert (l32 - l16).abs().max() < 5e-2
