@@ -106,6 +106,60 @@ __device__ __forceinline__ float softplus(float x) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 -- two fp32 lanes per issue slot)
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// 2^x for a pair of x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest range reduction by the
+// 1.5*2^23 magic add, degree-4 polynomial for 2^f on [-0.5, 0.5] with p(0) = 1 exactly (so slowly
+// decaying states do not drift: relative error ~ |f| * 2.3e-5 near 0, 2.9e-6 worst case), exponent
+// inserted by an integer shift-add.  x is clamped at -126 (result ~ 1e-38, i.e. 0 for the recurrence).
+__device__ __forceinline__ f32x2 exp2_poly2(f32x2 x2) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  x2 = pack2(x0, x1);
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f);
+  const f32x2 r2 = add2(x2, magic);                                  // magic + rint(x)
+  const f32x2 n2 = add2(r2, pack2(-12582912.0f, -12582912.0f));      // rint(x)
+  const f32x2 f2 = fma2(n2, pack2(-1.0f, -1.0f), x2);                // x - rint(x) in [-0.5, 0.5]
+  f32x2 p = fma2(pack2(0.009582849219441414f, 0.009582849219441414f), f2, pack2(0.05590642988681793f, 0.05590642988681793f));
+  p = fma2(p, f2, pack2(0.24024099111557007f, 0.24024099111557007f));
+  p = fma2(p, f2, pack2(0.6931241750717163f, 0.6931241750717163f));
+  p = fma2(p, f2, pack2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack2(p, p0, p1);
+  unpack2(r2, r0, r1);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+  return pack2(p0, p1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

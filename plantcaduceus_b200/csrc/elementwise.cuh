@@ -132,18 +132,23 @@ add_rmsnorm_kernel(const T* __restrict__ x, const RT* __restrict__ res_in, const
 // x: [S*L, *] with row pitch ldx (the x half of xz).  4 channels per thread, TT timesteps per thread,
 // sliding 7-row register window.  out_f[t] = SiLU(b_f + sum_k w_f[k] x[t-3+k]);
 // out_r[t] = SiLU(b_r + sum_k w_r[k] x[t+3-k])  (the causal conv of the time-reversed sequence).
-constexpr int kConvTT = 32;
+constexpr int kConvTT = 64;   // timesteps per thread (halo re-read: 6 / 64)
+constexpr int kConvBlk = 8;   // rows fetched per batch of back-to-back loads
+
+template <typename T> struct Raw4;               // 4 channels as loaded from memory
+template <> struct Raw4<bf16> { typedef uint2 type; };
+template <> struct Raw4<float> { typedef float4 type; };
 
 template <typename T>
-__device__ __forceinline__ void load4(const T* p, float (&v)[4]) {
-  if constexpr (sizeof(T) == 2) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(p);
-    v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
-    v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
-  } else {
-    const float4 raw = *reinterpret_cast<const float4*>(p);
-    v[0] = raw.x; v[1] = raw.y; v[2] = raw.z; v[3] = raw.w;
-  }
+__device__ __forceinline__ typename Raw4<T>::type load4_raw(const T* p) {
+  return *reinterpret_cast<const typename Raw4<T>::type*>(p);
+}
+__device__ __forceinline__ void cvt4(const uint2& raw, float (&v)[4]) {
+  v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
+  v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
+}
+__device__ __forceinline__ void cvt4(const float4& raw, float (&v)[4]) {
+  v[0] = raw.x; v[1] = raw.y; v[2] = raw.z; v[3] = raw.w;
 }
 template <typename T>
 __device__ __forceinline__ void store4(T* p, const float (&v)[4]) {
@@ -162,6 +167,7 @@ __global__ void __launch_bounds__(128)
 conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ w_f, const float* __restrict__ b_f,
                  const float* __restrict__ w_r, const float* __restrict__ b_r, T* __restrict__ out_f,
                  T* __restrict__ out_r, int L, int E) {
+  typedef typename Raw4<T>::type raw_t;
   const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (e0 >= E) return;
   const int t0 = blockIdx.y * kConvTT;
@@ -176,42 +182,58 @@ conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict
     bf[c] = b_f[e0 + c];
     br[c] = b_r[e0 + c];
   }
-  // win[j] holds x[t - 3 + j], j = 0..6
+  const T* xcol = x + e0;
+  raw_t zero_raw;
+  memset(&zero_raw, 0, sizeof(zero_raw));
+  auto fetch = [&](int t) -> raw_t {   // row t of this sequence, zero outside [0, L)
+    return (t >= 0 && t < L) ? load4_raw<T>(xcol + (seq_row0 + t) * ldx) : zero_raw;
+  };
+  // win[j] holds x[t - 3 + j], j = 0..6, for the step being computed
   float win[7][4];
+  raw_t nxt[kConvBlk];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int t = t0 - 3 + j;
-    if (t >= 0 && t < L) load4<T>(x + (seq_row0 + t) * ldx + e0, win[j]);
-    else { win[j][0] = win[j][1] = win[j][2] = win[j][3] = 0.f; }
-  }
-#pragma unroll 4
-  for (int i = 0; i < kConvTT; ++i) {
-    const int t = t0 + i;
-    if (t >= L) break;
-    if (t + 3 < L) load4<T>(x + (seq_row0 + t + 3) * ldx + e0, win[6]);
-    else { win[6][0] = win[6][1] = win[6][2] = win[6][3] = 0.f; }
-    float of[4], orv[4];
+  for (int j = 0; j < 6; ++j) cvt4(fetch(t0 - 3 + j), win[j]);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float a = bf[c];
-      a = fmaf(wf[c][0], win[0][c], a);
-      a = fmaf(wf[c][1], win[1][c], a);
-      a = fmaf(wf[c][2], win[2][c], a);
-      a = fmaf(wf[c][3], win[3][c], a);
-      of[c] = silu<PRECISE>(a);
-      float r = br[c];
-      r = fmaf(wr[c][0], win[6][c], r);
-      r = fmaf(wr[c][1], win[5][c], r);
-      r = fmaf(wr[c][2], win[4][c], r);
-      r = fmaf(wr[c][3], win[3][c], r);
-      orv[c] = silu<PRECISE>(r);
+  for (int i = 0; i < kConvBlk; ++i) nxt[i] = fetch(t0 + 3 + i);
+#pragma unroll 1
+  for (int blk = 0; blk < kConvTT; blk += kConvBlk) {
+    if (t0 + blk >= L) break;
+    raw_t cur[kConvBlk];
+#pragma unroll
+    for (int i = 0; i < kConvBlk; ++i) cur[i] = nxt[i];
+    if (blk + kConvBlk < kConvTT) {   // next batch of rows: in flight while this batch is computed
+#pragma unroll
+      for (int i = 0; i < kConvBlk; ++i) nxt[i] = fetch(t0 + blk + kConvBlk + 3 + i);
     }
-    store4<T>(out_f + (seq_row0 + t) * E + e0, of);
-    store4<T>(out_r + (seq_row0 + t) * E + e0, orv);
 #pragma unroll
-    for (int j = 0; j < 6; ++j)
+    for (int i = 0; i < kConvBlk; ++i) {
+      const int t = t0 + blk + i;
+      cvt4(cur[i], win[6]);
+      if (t < L) {
+        float of[4], orv[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) win[j][c] = win[j + 1][c];
+        for (int c = 0; c < 4; ++c) {
+          float a = bf[c];
+          a = fmaf(wf[c][0], win[0][c], a);
+          a = fmaf(wf[c][1], win[1][c], a);
+          a = fmaf(wf[c][2], win[2][c], a);
+          a = fmaf(wf[c][3], win[3][c], a);
+          of[c] = silu<PRECISE>(a);
+          float r = br[c];
+          r = fmaf(wr[c][0], win[6][c], r);
+          r = fmaf(wr[c][1], win[5][c], r);
+          r = fmaf(wr[c][2], win[4][c], r);
+          r = fmaf(wr[c][3], win[3][c], r);
+          orv[c] = silu<PRECISE>(r);
+        }
+        store4<T>(out_f + (seq_row0 + t) * E + e0, of);
+        store4<T>(out_r + (seq_row0 + t) * E + e0, orv);
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) win[j][c] = win[j + 1][c];
+    }
   }
 }
 
