@@ -129,6 +129,12 @@ int64_t pcad_launch_count(const pcad_handle* h);
 int pcad_op_linear(const void* A, const void* W, void* C, int64_t M, int N, int K,
                    int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream);
 
+/* C[M,N] = softplus(A W^T + bias[N]) (identity above 20), bf16 only: Mamba.dt_proj with the scan's
+ * delta_bias / delta_softplus step [selective_scan_fn(..., delta_bias, delta_softplus=True)] applied in the GEMM
+ * epilogue.  The result feeds pcad_op_biscan with delta_final = 1. */
+int pcad_op_linear_softplus(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
+                            int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream);
+
 /* Fused residual add + RMSNorm [mamba_ssm rms_norm_fn, prenorm=True]:
  * res_out = x + res_in (res_in may be NULL); y = res_out * rsqrt(mean(res_out^2) + eps) * w.
  * res_dtype is the storage type of res_in/res_out (PCAD_F32 iff residual_in_fp32).  res_out may be
@@ -149,13 +155,16 @@ int pcad_op_conv_silu(const void* x, int64_t ldx, const float* w_f, const float*
  * [BiMambaWrapper, strategy "add"]:
  *   u_*, delta_*: [S*L, E];  bc_*: [S*L, ldbc] with B at columns [bc_off, bc_off+16) and C at
  *   [bc_off+16, bc_off+32);  z: [S*L, E] with row pitch ldz;  A_*: float [E, 16] (= -exp(A_log));
- *   D_*, dt_bias_*: float [E];  y: [S*L, E]. */
+ *   D_*, dt_bias_*: float [E];  y: [S*L, E].
+ *   delta_final = 0: delta_* are raw dt_proj outputs, the kernel applies softplus(delta + dt_bias) itself (the
+ *   reference's order of operations);  delta_final = 1: delta_* already hold softplus(dt_proj + dt_bias)
+ *   (pcad_op_linear_softplus) and dt_bias_* are ignored. */
 int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f,
                    const void* u_r, const void* delta_r, const void* bc_r,
                    int64_t ldbc, int bc_off, const void* z, int64_t ldz,
                    const float* A_f, const float* D_f, const float* dt_bias_f,
                    const float* A_r, const float* D_r, const float* dt_bias_r,
-                   void* y, int S, int L, int E, int dtype, void* stream);
+                   void* y, int S, int L, int E, int delta_final, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -207,12 +207,13 @@ struct StageTimer {
 
 // ---- operator launchers (shared by the forward pass and the pcad_op_* entry points) -------------
 int op_linear(pcad_handle* h, const void* A, const void* W, void* C, long long M, int N, int K, long long lda,
-              long long ldw, long long ldc, bool f32, int num_sms, cudaStream_t st) {
+              long long ldw, long long ldc, bool f32, int num_sms, cudaStream_t st, const float* softplus_bias = nullptr) {
   if (f32) {
+    if (softplus_bias) return fail(h, PCAD_ERR_INVALID, "the softplus epilogue exists for bf16 only");
     CUDA_TRY(h, gemm_f32_simt(static_cast<const float*>(A), static_cast<const float*>(W), static_cast<float*>(C), M, N, K, lda, ldw, ldc, st));
   } else {
     const char* why = nullptr;
-    cudaError_t e = gemm_bf16_tcgen05(static_cast<const bf16*>(A), static_cast<const bf16*>(W), static_cast<bf16*>(C), M, N, K, lda, ldw, ldc, num_sms, st, &why);
+    cudaError_t e = gemm_bf16_tcgen05(static_cast<const bf16*>(A), static_cast<const bf16*>(W), static_cast<bf16*>(C), M, N, K, lda, ldw, ldc, num_sms, st, &why, softplus_bias);
     if (e != cudaSuccess) return fail(h, why ? PCAD_ERR_INVALID : PCAD_ERR_CUDA, "%s", why ? why : cudaGetErrorString(e));
   }
   return PCAD_OK;
@@ -261,23 +262,20 @@ int op_conv(pcad_handle* h, const void* x, long long ldx, const float* w_f, cons
 int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* bc_f, const void* u_r,
               const void* delta_r, const void* bc_r, long long ldbc, int bc_off, const void* z, long long ldz,
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
-              const float* bias_r, void* y, int S, int L, int E, bool f32, cudaStream_t st) {
+              const float* bias_r, void* y, int S, int L, int E, bool f32, bool delta_final, cudaStream_t st) {
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
     return fail(h, PCAD_ERR_INVALID, "biscan: E, ldbc, bc_off, ldz must be multiples of %d elements", vec);
   if (S <= 0 || L <= 0) return PCAD_OK;
   if (S > 65535) return fail(h, PCAD_ERR_INVALID, "biscan: at most 65535 sequences per call");
   cudaError_t e;
-  if (f32)
-    e = launch_biscan<float, true>(static_cast<const float*>(u_f), static_cast<const float*>(delta_f), static_cast<const float*>(bc_f),
-                                   static_cast<const float*>(u_r), static_cast<const float*>(delta_r), static_cast<const float*>(bc_r),
-                                   ldbc, bc_off, static_cast<const float*>(z), ldz, A_f, D_f, bias_f, A_r, D_r, bias_r,
-                                   static_cast<float*>(y), S, L, E, st);
-  else
-    e = launch_biscan<bf16, false>(static_cast<const bf16*>(u_f), static_cast<const bf16*>(delta_f), static_cast<const bf16*>(bc_f),
-                                   static_cast<const bf16*>(u_r), static_cast<const bf16*>(delta_r), static_cast<const bf16*>(bc_r),
-                                   ldbc, bc_off, static_cast<const bf16*>(z), ldz, A_f, D_f, bias_f, A_r, D_r, bias_r,
-                                   static_cast<bf16*>(y), S, L, E, st);
+#define PCAD_SCAN_ARGS(TT)                                                                                           \
+  static_cast<const TT*>(u_f), static_cast<const TT*>(delta_f), static_cast<const TT*>(bc_f), static_cast<const TT*>(u_r), \
+      static_cast<const TT*>(delta_r), static_cast<const TT*>(bc_r), ldbc, bc_off, static_cast<const TT*>(z), ldz, A_f, D_f, \
+      bias_f, A_r, D_r, bias_r, static_cast<TT*>(y), S, L, E, st
+  if (f32) e = delta_final ? launch_biscan<float, true, true>(PCAD_SCAN_ARGS(float)) : launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float));
+  else e = delta_final ? launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16)) : launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16));
+#undef PCAD_SCAN_ARGS
   CUDA_TRY(h, e);
   return PCAD_OK;
 }
@@ -372,6 +370,9 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
       }
       {
         StageTimer tm(h, st, PCAD_ST_DT_PROJ);
+        // The softplus(dt_proj + bias) GEMM epilogue (pcad_op_linear_softplus + delta_final scan) was measured
+        // slower end to end on B200 (dt_proj 0.21 -> 0.50 ms, scan 5.57 -> 5.42 ms per l32 layer at B = 256), so
+        // the forward keeps the reference's order: raw dt_proj output, softplus inside the scan.
         rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, f32, h->num_sms, st);
         if (rc) return rc;
       }
@@ -380,7 +381,8 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
       StageTimer tm(h, st, PCAD_ST_SCAN);
       const uint8_t* zbase = static_cast<const uint8_t*>(ws.xz) + static_cast<size_t>(E) * h->act_size;
       rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
-                     lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st);
+                     lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
+                     /*delta_final=*/false, st);
       if (rc) return rc;
     }
     {
@@ -809,6 +811,11 @@ int pcad_op_linear(const void* A, const void* W, void* C, int64_t M, int N, int 
   return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, dtype == PCAD_F32, op_num_sms(), static_cast<cudaStream_t>(stream)));
 }
 
+int pcad_op_linear_softplus(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 || !bias) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), bias));
+}
+
 int pcad_op_add_rmsnorm(const void* x, const void* res_in, const float* w, void* y, void* res_out, int64_t rows, int d, float eps, int dtype, int res_dtype, void* stream) {
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   if (dtype == PCAD_F32 && res_dtype != PCAD_F32) return PCAD_ERR_INVALID;
@@ -822,10 +829,10 @@ int pcad_op_conv_silu(const void* x, int64_t ldx, const float* w_f, const float*
 
 int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f, const void* u_r, const void* delta_r, const void* bc_r,
                    int64_t ldbc, int bc_off, const void* z, int64_t ldz, const float* A_f, const float* D_f, const float* dt_bias_f,
-                   const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E, int dtype, void* stream) {
+                   const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E, int delta_final, int dtype, void* stream) {
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_biscan(op_scratch(), u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
-                                     A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream)));
+                                     A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, delta_final != 0, static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

@@ -1,57 +1,58 @@
 // Bidirectional selective scan (Mamba-1, d_state = 16) with softplus(delta + bias), D skip and SiLU(z)
-// gate; the forward-in-time and backward-in-time scans of BiMambaWrapper (strategy "add") run in the
-// same thread and meet in the middle, so their sum is formed without a flipped copy and written once.
+// gate; the forward-in-time and backward-in-time scans of BiMambaWrapper (strategy "add") run side by side in
+// one CTA and meet in the middle, so their sum is formed without a flipped copy and y is written once.
 //
 //   [EXT] mamba_ssm selective_scan_fn(u, delta, A, B, C, D, z, delta_bias, delta_softplus=True)
 //   [EXT] Caduceus BiMambaWrapper.forward: mamba_fwd(u) + flip_L(mamba_rev(flip_L(u)))
 //
-// Work decomposition: one CTA = one sequence s x 128 channels; one thread = one channel, holding the
-// 2 x 16 fp32 states and the 2 x 16 A coefficients in registers.  Step i advances the forward scan
-// at t_f = i and the reverse scan at t_r = L-1-i.  Until the two meet, each direction parks its un-gated
-// partial output in y; after they cross, a direction reads the other's partial (written earlier by this
-// same thread), adds its own, applies the gate and stores the final value.
-// Inputs are streamed in chunks of 16 timesteps through a 2-stage cp.async ring (u, delta for both
-// directions, z when a chunk finalises, and the 32 B/C values per timestep, which are converted to fp32
-// once per chunk and then broadcast-read by all 128 threads).
+// Work decomposition: one CTA = one sequence x 128 channels; 256 threads: warps 0-3 run the forward scan,
+// warps 4-7 the reverse scan, one thread = one (direction, channel) holding its 16 fp32 states and 16 A
+// coefficients in registers.  (Keeping both directions in one thread needs ~126 registers, i.e. 4 warps per
+// scheduler, and the kernel is latency-bound there; one direction per thread fits 6 warps per scheduler.)
+// Step i advances the forward scan at t_f = i and the reverse scan at t_r = L-1-i.  Inputs are streamed in chunks
+// of 16 steps through a 2-stage cp.async ring; the 32 B/C values per step are converted to fp32 once per chunk
+// and broadcast-read.  Each thread leaves its un-gated y for the chunk in shared memory; a vectorised chunk
+// epilogue then either parks the partial in y (the other direction has not reached that position yet) or adds the
+// other direction's parked partial, applies SiLU(z) and stores the final value -- 16-byte global accesses only.
 //
-// The bf16 kernel is bound by the MUFU (ex2) pipe and by issue slots, not by HBM (ncu: profiles/).  Its
-// inner loop therefore (a) keeps (n, n+1) state pairs in 64-bit registers and uses the packed fp32x2
-// instructions of sm_100 (FFMA2 / FMUL2: two lanes per issue slot), (b) takes kScanPoly of the 8
-// pair-exponentials per direction from an FMA-pipe polynomial instead of MUFU.EX2, (c) works in the
-// log2 domain end to end: d' = log2(1 + 2^((delta + bias) log2 e)), exp(d A) = 2^(d' A), and the ln 2 that
-// d = d' ln 2 owes to the input term is folded into B when B is converted to fp32.
+// The bf16 kernel is bound by the MUFU (ex2) and FMA pipes, not by HBM (ncu: profiles/).  Its inner loop
+// (a) keeps (n, n+1) state pairs in 64-bit registers and uses the packed fp32x2 instructions of sm_100
+// (FFMA2 / FMUL2: two lanes per issue slot), (b) takes kScanPoly of the 8 pair-exponentials from an FMA-pipe
+// polynomial instead of MUFU.EX2, (c) works in the log2 domain end to end: d' = log2(1 + 2^((delta + bias) log2 e)),
+// exp(d A) = 2^(d' A), and the ln 2 that d = d' ln 2 owes to the input term is folded into B when B is converted.
 #pragma once
+
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace pcad {
 
-constexpr int kScanTC = 16;    // timesteps per chunk
-constexpr int kScanCH = 128;   // channels (threads) per CTA
-constexpr int kScanN = 16;     // d_state
+constexpr int kScanTC = 16;      // timesteps per chunk
+constexpr int kScanCH = 128;     // channels per CTA
+constexpr int kScanThreads = 2 * kScanCH;
+constexpr int kScanN = 16;       // d_state
 #ifndef PCAD_SCAN_POLY
-#define PCAD_SCAN_POLY 3
+#define PCAD_SCAN_POLY 1
 #endif
-constexpr int kScanPoly = PCAD_SCAN_POLY;   // pairs (of 8) per direction whose exp2 runs on the FMA pipe
+constexpr int kScanPoly = PCAD_SCAN_POLY;   // pairs (of 8) whose exp2 runs on the FMA pipe
+#ifndef PCAD_SCAN_MINBLOCKS
+#define PCAD_SCAN_MINBLOCKS 3
+#endif
 
 template <typename T>
-struct ScanSmem {
-  // per stage
-  T uf[kScanTC][kScanCH];
-  T df[kScanTC][kScanCH];
-  T ur[kScanTC][kScanCH];
-  T dr[kScanTC][kScanCH];
-  T zf[kScanTC][kScanCH];
-  T zr[kScanTC][kScanCH];
-  T bcf_raw[kScanTC][2 * kScanN];
-  T bcr_raw[kScanTC][2 * kScanN];
+struct ScanStage {
+  T u[2][kScanTC][kScanCH];          // [direction][step][channel]
+  T d[2][kScanTC][kScanCH];
+  T bc_raw[2][kScanTC][2 * kScanN];
 };
 
 template <typename T>
 struct ScanShared {
-  ScanSmem<T> st[2];
-  float bcf[kScanTC][2 * kScanN];  // fp32 B|C of the chunk being computed
-  float bcr[kScanTC][2 * kScanN];
+  ScanStage<T> st[2];
+  float bc[2][kScanTC][2 * kScanN];   // fp32 B|C of the chunk being computed
+  float ys[2][kScanTC][kScanCH];      // un-gated outputs of the chunk, per direction
+  T pz[2][2][kScanTC][kScanCH];       // [partial | z][direction][step][channel]: prefetched for the chunk epilogue
 };
 
 // One direction's 16 states of one channel.  step() advances h <- exp(d*A) h + du*B and returns
@@ -69,6 +70,7 @@ template <> struct ScanDir<true> {
   static __device__ __forceinline__ float b_scale() { return 1.0f; }
   // returns d (natural units)
   __device__ __forceinline__ float delta(float raw) const { return softplus<true>(raw + bias); }
+  __device__ __forceinline__ float delta_final(float d) const { return d; }
   __device__ __forceinline__ float step(float d, float du, float y0, const float* bc) {
     float y = y0;
 #pragma unroll
@@ -81,7 +83,7 @@ template <> struct ScanDir<true> {
 };
 
 template <> struct ScanDir<false> {
-  f32x2 h[kScanN / 2], a[kScanN / 2];
+  f32x2 h[kScanN / 2], a[kScanN / 2];   // a = A (log2 domain: multiplied by d' = d / ln 2)
   float bias_l2;   // bias * log2(e)
   __device__ __forceinline__ void init(const float* A, float bias_) {
     bias_l2 = bias_ * kLog2e;
@@ -98,6 +100,8 @@ template <> struct ScanDir<false> {
     const float sp = lg2_approx(1.0f + ex2_approx(xl));
     return xl > 20.0f * kLog2e ? xl : sp;
   }
+  // delta already softplus'ed (dt_proj's softplus epilogue): only the change of units
+  __device__ __forceinline__ float delta_final(float d) const { return d * kLog2e; }
   __device__ __forceinline__ float step(float d, float du, float y0, const float* bc) {
     const f32x2 dd = pack2(d, d), duu = pack2(du, du);
     const ulonglong2* bc2 = reinterpret_cast<const ulonglong2*>(bc);   // 16 bytes = two (n, n+1) pairs
@@ -131,70 +135,9 @@ template <> struct ScanDir<false> {
   }
 };
 
-enum ScanMode { kScanPark = 0, kScanFinal = 1, kScanMixed = 2 };
-
-// One chunk of up to kScanTC steps.  PARK: every step has t_f < t_r (store un-gated partials).
-// FINAL: every step has t_f > t_r (add the parked partial of the other direction, gate, store).
-// MIXED: decide per step (the chunk that contains the meeting point when it is not chunk-aligned).
-template <typename T, bool PRECISE, int MODE>
-__device__ __forceinline__ void scan_chunk(ScanDir<PRECISE>& Sf, ScanDir<PRECISE>& Sr, const ScanSmem<T>& s,
-                                           const float (*bcf)[2 * kScanN], const float (*bcr)[2 * kScanN], float Df,
-                                           float Dr, T* yf_ptr, T* yr_ptr, long long E, int i0, int nsteps, int L,
-                                           int tid) {
-  // FINAL: the other direction's parked partials are fetched one step ahead and kept as raw bits; the
-  // conversion sits at the point of use so the load has a whole step to land.
-  T p1r = T(), p2r = T();
-  if (MODE == kScanFinal) {
-    p1r = *yf_ptr;
-    p2r = *yr_ptr;
-  }
-#pragma unroll 1
-  for (int j = 0; j < nsteps; ++j) {
-    T p1n = T(), p2n = T();
-    if (MODE == kScanFinal && j + 1 < nsteps) {
-      p1n = yf_ptr[E];
-      p2n = *(yr_ptr - E);
-    }
-    const float u1 = ActT<T>::to_f(s.uf[j][tid]);
-    const float d1 = Sf.delta(ActT<T>::to_f(s.df[j][tid]));
-    const float u2 = ActT<T>::to_f(s.ur[j][tid]);
-    const float d2 = Sr.delta(ActT<T>::to_f(s.dr[j][tid]));
-    const float y1 = Sf.step(d1, d1 * u1, Df * u1, bcf[j]);
-    const float y2 = Sr.step(d2, d2 * u2, Dr * u2, bcr[j]);
-    if (MODE == kScanPark) {
-      *yf_ptr = ActT<T>::from_f(y1);
-      *yr_ptr = ActT<T>::from_f(y2);
-    } else if (MODE == kScanFinal) {
-      const float z1 = ActT<T>::to_f(s.zf[j][tid]);
-      const float z2 = ActT<T>::to_f(s.zr[j][tid]);
-      *yf_ptr = ActT<T>::from_f((y1 + ActT<T>::to_f(p1r)) * silu<PRECISE>(z1));
-      *yr_ptr = ActT<T>::from_f((y2 + ActT<T>::to_f(p2r)) * silu<PRECISE>(z2));
-      p1r = p1n;
-      p2r = p2n;
-    } else {
-      const int tf = i0 + j, tr = L - 1 - tf;
-      if (tf < tr) {
-        *yf_ptr = ActT<T>::from_f(y1);
-        *yr_ptr = ActT<T>::from_f(y2);
-      } else if (tf == tr) {
-        const float zz = ActT<T>::to_f(s.zf[j][tid]);
-        *yf_ptr = ActT<T>::from_f((y1 + y2) * silu<PRECISE>(zz));
-      } else {
-        const float q1 = ActT<T>::to_f(*yf_ptr);  // reverse-direction partial parked at tf
-        const float q2 = ActT<T>::to_f(*yr_ptr);  // forward-direction partial parked at tr
-        const float z1 = ActT<T>::to_f(s.zf[j][tid]);
-        const float z2 = ActT<T>::to_f(s.zr[j][tid]);
-        *yf_ptr = ActT<T>::from_f((y1 + q1) * silu<PRECISE>(z1));
-        *yr_ptr = ActT<T>::from_f((y2 + q2) * silu<PRECISE>(z2));
-      }
-    }
-    yf_ptr += E;
-    yr_ptr -= E;
-  }
-}
-
-template <typename T, bool PRECISE>
-__global__ void __launch_bounds__(kScanCH)
+// DFINAL: delta_* already hold softplus(dt_proj + bias) (the GEMM's softplus epilogue); bias_* are ignored.
+template <typename T, bool PRECISE, bool DFINAL>
+__global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : PCAD_SCAN_MINBLOCKS)
 biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T* __restrict__ bc_f,
               const T* __restrict__ u_r, const T* __restrict__ delta_r, const T* __restrict__ bc_r, long long ldbc,
               int bc_off, const T* __restrict__ z, long long ldz, const float* __restrict__ A_f,
@@ -204,54 +147,51 @@ biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T*
   ScanShared<T>& sm = *reinterpret_cast<ScanShared<T>*>(scan_smem_raw);
 
   const int tid = threadIdx.x;
+  const int dir = tid >> 7;               // warp-uniform: warps 0-3 forward, 4-7 reverse
+  const int ch = tid & (kScanCH - 1);
   const int e0 = blockIdx.x * kScanCH;
-  const int e = e0 + tid;
+  const int e = e0 + ch;
   const bool active = e < E;
   const long long row0 = static_cast<long long>(blockIdx.y) * L;
   const int nch = (L + kScanTC - 1) / kScanTC;
-  constexpr int VEC = 16 / sizeof(T);              // elements per 16-byte cp.async
+  constexpr int VEC = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int SEGS = kScanCH / VEC;              // 16-byte segments per 128-channel row
   constexpr int BCSEGS = 2 * kScanN / VEC;         // 16-byte segments per B|C row
 
-  // chunk c: forward rows [16c, 16c+16), reverse rows [L-16c-16, L-16c); row j of the stage buffers holds
-  // forward timestep 16c + j and reverse timestep L-1-(16c + j).
+  // chunk c, stage row j: forward timestep 16c + j, reverse timestep L-1-(16c + j).
   auto issue = [&](int c, int stage) {
-    ScanSmem<T>& s = sm.st[stage];
-    const bool fin = (2 * kScanTC * c + 2 * kScanTC - 1 >= L - 1);  // chunk may finalise -> needs z
-    for (int idx = tid; idx < kScanTC * SEGS; idx += kScanCH) {
-      const int j = idx / SEGS, seg = idx % SEGS;
+    ScanStage<T>& s = sm.st[stage];
+    for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
+      const int dd = idx / (kScanTC * SEGS);
+      const int rem = idx - dd * (kScanTC * SEGS);
+      const int j = rem / SEGS, seg = rem % SEGS;
       const int i = c * kScanTC + j;
-      const int ch = e0 + seg * VEC;
-      const bool ok = (i < L) && (ch < E);
-      const long long rf = row0 + (ok ? i : 0);
-      const long long rr = row0 + (ok ? (L - 1 - i) : 0);
-      const int chs = ok ? ch : 0;
+      const int chn = e0 + seg * VEC;
+      const bool ok = (i < L) && (chn < E);
+      const long long r = row0 + (ok ? (dd ? (L - 1 - i) : i) : 0);
+      const int chs = ok ? chn : 0;
       const int nb = ok ? 16 : 0;
-      cp_async16(&s.uf[j][seg * VEC], u_f + rf * E + chs, nb);
-      cp_async16(&s.df[j][seg * VEC], delta_f + rf * E + chs, nb);
-      cp_async16(&s.ur[j][seg * VEC], u_r + rr * E + chs, nb);
-      cp_async16(&s.dr[j][seg * VEC], delta_r + rr * E + chs, nb);
-      if (fin) {
-        cp_async16(&s.zf[j][seg * VEC], z + rf * ldz + chs, nb);
-        cp_async16(&s.zr[j][seg * VEC], z + rr * ldz + chs, nb);
-      }
+      cp_async16(&s.u[dd][j][seg * VEC], (dd ? u_r : u_f) + r * E + chs, nb);
+      cp_async16(&s.d[dd][j][seg * VEC], (dd ? delta_r : delta_f) + r * E + chs, nb);
     }
-    for (int idx = tid; idx < kScanTC * BCSEGS; idx += kScanCH) {
-      const int j = idx / BCSEGS, seg = idx % BCSEGS;
+    for (int idx = tid; idx < 2 * kScanTC * BCSEGS; idx += kScanThreads) {
+      const int dd = idx / (kScanTC * BCSEGS);
+      const int rem = idx - dd * (kScanTC * BCSEGS);
+      const int j = rem / BCSEGS, seg = rem % BCSEGS;
       const int i = c * kScanTC + j;
       const bool ok = i < L;
-      const long long rf = row0 + (ok ? i : 0);
-      const long long rr = row0 + (ok ? (L - 1 - i) : 0);
-      const int nb = ok ? 16 : 0;
-      cp_async16(&s.bcf_raw[j][seg * VEC], bc_f + rf * ldbc + bc_off + seg * VEC, nb);
-      cp_async16(&s.bcr_raw[j][seg * VEC], bc_r + rr * ldbc + bc_off + seg * VEC, nb);
+      const long long r = row0 + (ok ? (dd ? (L - 1 - i) : i) : 0);
+      cp_async16(&s.bc_raw[dd][j][seg * VEC], (dd ? bc_r : bc_f) + r * ldbc + bc_off + seg * VEC, ok ? 16 : 0);
     }
   };
 
-  ScanDir<PRECISE> Sf, Sr;
-  Sf.init(active ? A_f + e * kScanN : nullptr, active ? bias_f[e] : 0.f);
-  Sr.init(active ? A_r + e * kScanN : nullptr, active ? bias_r[e] : 0.f);
-  const float Df = active ? D_f[e] : 0.f, Dr = active ? D_r[e] : 0.f;
+  ScanDir<PRECISE> S;
+  {
+    const float* A = dir ? A_r : A_f;
+    const float* bias = dir ? bias_r : bias_f;
+    S.init(active ? A + e * kScanN : nullptr, active ? bias[e] : 0.f);
+  }
+  const float Dskip = active ? (dir ? D_r : D_f)[e] : 0.f;
   const float bscale = ScanDir<PRECISE>::b_scale();
 
   issue(0, 0);
@@ -265,51 +205,111 @@ biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T*
     } else {
       cp_async_wait<0>();
     }
-    __syncthreads();
-    ScanSmem<T>& s = sm.st[stage];
+    __syncthreads();   // chunk c has landed; the previous chunk's epilogue is done with sm.ys / sm.pz
+    const ScanStage<T>& s = sm.st[stage];
+    const int i0 = c * kScanTC;
+    const int nsteps = min(kScanTC, L - i0);
+    // Positions of this chunk that the other direction visited in an EARLIER chunk will be finalised in the
+    // epilogue: fetch their parked partials and z rows now (every earlier epilogue is complete and visible after
+    // the barrier above), so that the epilogue does not wait on global memory.
+    const bool has_final = (L - 1 - (i0 + nsteps - 1)) < i0 + nsteps;
+    if (has_final) {
+      for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
+        const int dd = idx / (kScanTC * SEGS);
+        const int rem = idx - dd * (kScanTC * SEGS);
+        const int j = rem / SEGS, seg = rem % SEGS;
+        const int i = i0 + j, io = L - 1 - i;
+        const int chn = e0 + seg * VEC;
+        const bool ok = (j < nsteps) && (chn < E) && (io < i0 + nsteps);
+        const long long r = row0 + (ok ? (dd ? io : i) : 0);
+        const int chs = ok ? chn : 0;
+        if (ok && io < i0) cp_async16(&sm.pz[0][dd][j][seg * VEC], y + r * E + chs, 16);
+        if (ok) cp_async16(&sm.pz[1][dd][j][seg * VEC], z + r * ldz + chs, 16);
+      }
+    }
+    cp_async_commit();
     // B|C to fp32, once per chunk (B carries the ln 2 of the log2-domain delta on the fast path)
-    for (int idx = tid; idx < kScanTC * 2 * kScanN; idx += kScanCH) {
-      const int j = idx / (2 * kScanN), k = idx % (2 * kScanN);
-      const float sc = k < kScanN ? bscale : 1.0f;
-      sm.bcf[j][k] = ActT<T>::to_f(s.bcf_raw[j][k]) * sc;
-      sm.bcr[j][k] = ActT<T>::to_f(s.bcr_raw[j][k]) * sc;
+    for (int idx = tid; idx < 2 * kScanTC * 2 * kScanN; idx += kScanThreads) {
+      const int dd = idx / (kScanTC * 2 * kScanN);
+      const int rem = idx - dd * (kScanTC * 2 * kScanN);
+      const int j = rem / (2 * kScanN), k = rem % (2 * kScanN);
+      sm.bc[dd][j][k] = ActT<T>::to_f(s.bc_raw[dd][j][k]) * (k < kScanN ? bscale : 1.0f);
     }
     __syncthreads();
 
     if (active) {
-      const int i0 = c * kScanTC;
-      const int nsteps = min(kScanTC, L - i0);
-      T* yf_ptr = y + (row0 + i0) * E + e;
-      T* yr_ptr = y + (row0 + (L - 1 - i0)) * E + e;
-      const int ilast = i0 + nsteps - 1;
-      if (2 * ilast < L - 1)
-        scan_chunk<T, PRECISE, kScanPark>(Sf, Sr, s, sm.bcf, sm.bcr, Df, Dr, yf_ptr, yr_ptr, E, i0, nsteps, L, tid);
-      else if (2 * i0 > L - 1)
-        scan_chunk<T, PRECISE, kScanFinal>(Sf, Sr, s, sm.bcf, sm.bcr, Df, Dr, yf_ptr, yr_ptr, E, i0, nsteps, L, tid);
-      else
-        scan_chunk<T, PRECISE, kScanMixed>(Sf, Sr, s, sm.bcf, sm.bcr, Df, Dr, yf_ptr, yr_ptr, E, i0, nsteps, L, tid);
+      const T* up = &s.u[dir][0][ch];
+      const T* dp = &s.d[dir][0][ch];
+      const float* bcp = &sm.bc[dir][0][0];
+      float* ysp = &sm.ys[dir][0][ch];
+#pragma unroll 1
+      for (int j = 0; j < nsteps; ++j) {
+        const float uu = ActT<T>::to_f(up[j * kScanCH]);
+        const float draw = ActT<T>::to_f(dp[j * kScanCH]);
+        const float dl = DFINAL ? S.delta_final(draw) : S.delta(draw);
+        ysp[j * kScanCH] = S.step(dl, dl * uu, Dskip * uu, bcp + j * 2 * kScanN);
+      }
     }
-    __syncthreads();  // everyone is done with this stage (and sm.bc*) before it is refilled
+    cp_async_wait<0>();
+    __syncthreads();   // both directions' un-gated outputs of the chunk are in sm.ys, partials / z in sm.pz
+
+    // ---- chunk epilogue: 16-byte vectors; item = (direction, step, segment of VEC channels)
+    for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
+      const int dd = idx / (kScanTC * SEGS);
+      const int rem = idx - dd * (kScanTC * SEGS);
+      const int j = rem / SEGS, seg = rem % SEGS;
+      const int chn = e0 + seg * VEC;
+      if (j >= nsteps || chn >= E) continue;
+      const int i = i0 + j;                 // this direction's step index
+      const int io = L - 1 - i;             // step at which the OTHER direction visits the same position
+      const int t = dd ? io : i;            // the position itself
+      float v[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] = sm.ys[dd][j][seg * VEC + k];
+      T* yp = y + (row0 + t) * E + chn;
+      if (io >= i0 + nsteps) {              // the other direction comes later: park the partial
+        store16<T>(yp, v);
+        continue;
+      }
+      if (io >= i0) {                       // both visits fall in this chunk: combine from shared memory, once
+        if (io > i || (io == i && dd == 1)) continue;   // the later visitor (forward on a tie) writes
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] += sm.ys[dd ^ 1][io - i0][seg * VEC + k];
+      } else {                              // parked in an earlier chunk (by another thread of this CTA)
+        float p[VEC];
+        load16<T>(&sm.pz[0][dd][j][seg * VEC], p);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[k] += p[k];
+      }
+      float zz[VEC];
+      load16<T>(&sm.pz[1][dd][j][seg * VEC], zz);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] *= silu<PRECISE>(zz[k]);
+      store16<T>(yp, v);
+    }
+    // no barrier here: the next iteration's first __syncthreads orders these reads of sm.ys and of the stage
+    // against their next writers
   }
 }
 
-template <typename T, bool PRECISE>
+template <typename T, bool PRECISE, bool DFINAL>
 inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, const T* u_r, const T* delta_r,
                                  const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
                                  const float* D_r, const float* bias_r, T* y, int S, int L, int E,
                                  cudaStream_t stream) {
-  const size_t smem = sizeof(ScanShared<T>);
+  size_t smem = sizeof(ScanShared<T>);
+  if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(biscan_kernel<T, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e1 = cudaFuncSetAttribute(biscan_kernel<T, PRECISE, DFINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem));
     if (e1 != cudaSuccess) return e1;
     attr_set = true;
   }
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
-  biscan_kernel<T, PRECISE><<<grid, kScanCH, smem, stream>>>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z,
-                                                           ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E);
+  biscan_kernel<T, PRECISE, DFINAL><<<grid, kScanThreads, smem, stream>>>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z,
+                                                                ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E);
   return cudaGetLastError();
 }
 

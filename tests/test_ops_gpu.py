@@ -49,6 +49,23 @@ def test_linear_bf16_tcgen05(lib, cuda_device, M, N, K):
     assert err <= tol, (err, tol)
 
 
+@pytest.mark.parametrize("M,N,K,lda", [(1024, 768, 24, 64), (777, 2048, 64, 96), (256, 128, 8, 48), (130, 104, 32, 32)])
+def test_linear_softplus_epilogue(lib, cuda_device, M, N, K, lda):
+    """dt_proj with the scan's delta_bias + softplus step applied in the GEMM epilogue (threshold 20 as the reference)."""
+    g = torch.Generator().manual_seed(M + N)
+    Abig = (torch.randn(M, lda, generator=g) * 2).to(cuda_device, torch.bfloat16)
+    W = torch.randn(N, K, generator=g).to(cuda_device, torch.bfloat16)
+    bias = (torch.randn(N, generator=g) * 3 - 2).to(cuda_device)
+    bias[0] = 25.0
+    Cout = torch.full((M, N), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    check(lib, lib.pcad_op_linear_softplus(ptr(Abig), ptr(W), ptr(bias), ptr(Cout), M, N, K, lda, K, N, BF16, stream()))
+    torch.cuda.synchronize()
+    want = F.softplus(Abig[:, :K].float() @ W.float().t() + bias[None, :])
+    got = Cout.float()
+    assert not torch.isnan(got).any()
+    assert torch.allclose(got, want, rtol=2 ** -7, atol=1e-6)
+
+
 def test_linear_bf16_strided(lib, cuda_device):
     """A taken as the first K columns of a wider matrix (dt_proj reads dt out of [T, R+2N])."""
     M, N, K, lda = 512, 768, 24, 64
@@ -128,9 +145,10 @@ def test_conv_silu_both_directions(lib, cuda_device, dtype, S, L, E):
     assert torch.allclose(orv.cpu().float(), want_r, **tol)
 
 
-@pytest.mark.parametrize("dtype", [F32, BF16])
-@pytest.mark.parametrize("S,L,E,R", [(2, 512, 256, 24), (3, 64, 128, 8), (2, 37, 128, 8), (1, 1, 128, 8), (2, 16, 128, 64), (1, 33, 384, 24)])
-def test_biscan(lib, cuda_device, dtype, S, L, E, R):
+@pytest.mark.parametrize("dtype,delta_final", [(F32, 0), (BF16, 0), (BF16, 1), (F32, 1)])
+@pytest.mark.parametrize("S,L,E,R", [(2, 512, 256, 24), (3, 64, 128, 8), (2, 37, 128, 8), (1, 1, 128, 8), (2, 16, 128, 64), (1, 33, 384, 24),
+                                     (1, 40, 128, 8), (1, 47, 200, 8)])
+def test_biscan(lib, cuda_device, dtype, delta_final, S, L, E, R):
     N = 16
     td = torch.float32 if dtype == F32 else torch.bfloat16
     g = torch.Generator().manual_seed(S * 100 + L)
@@ -145,14 +163,18 @@ def test_biscan(lib, cuda_device, dtype, S, L, E, R):
     bias = [mk(E) - 3 for _ in range(2)]
     bias[0][0] = 30.0   # exercises the softplus threshold branch
     dev = lambda t: t.to(cuda_device).contiguous()
-    u_d, dl_d, bc_d = [dev(t) for t in u], [dev(t) for t in dl], [dev(t) for t in bc]
+    if delta_final:   # the kernel receives softplus(delta + bias), rounded to the activation dtype, and ignores bias
+        dl_in = [F.softplus(dl[k].float() + bias[k][None, :]).to(td) for k in range(2)]
+    else:
+        dl_in = dl
+    u_d, dl_d, bc_d = [dev(t) for t in u], [dev(t) for t in dl_in], [dev(t) for t in bc]
     xz_d = dev(xz)
     A_d, D_d, b_d = [dev(t) for t in A], [dev(t) for t in D], [dev(t) for t in bias]
     y = torch.full((S * L, E), float("nan"), device=cuda_device, dtype=td)
     z_ptr = C.c_void_p(xz_d.data_ptr() + E * xz_d.element_size())
     check(lib, lib.pcad_op_biscan(ptr(u_d[0]), ptr(dl_d[0]), ptr(bc_d[0]), ptr(u_d[1]), ptr(dl_d[1]), ptr(bc_d[1]),
                                   RP, R, z_ptr, 2 * E, ptr(A_d[0]), ptr(D_d[0]), ptr(b_d[0]),
-                                  ptr(A_d[1]), ptr(D_d[1]), ptr(b_d[1]), ptr(y), S, L, E, dtype, stream()))
+                                  ptr(A_d[1]), ptr(D_d[1]), ptr(b_d[1]), ptr(y), S, L, E, delta_final, dtype, stream()))
     torch.cuda.synchronize()
 
     # oracle: two selective_scan_ref calls (fp32 maths on the same rounded inputs), reverse one flipped
@@ -162,6 +184,10 @@ def test_biscan(lib, cuda_device, dtype, S, L, E, R):
     ys = []
     for k in range(2):
         uu, dd = to_bel(u[k], E), to_bel(dl[k], E)
+        if delta_final:   # invert the softplus on the rounded value so selective_scan_ref reproduces exactly that delta
+            sp = dl_in[k].float()
+            raw = torch.where(sp > 20, sp, torch.log(torch.expm1(sp.double())).float())
+            dd = to_bel(raw - bias[k][None, :], E)
         Bm, Cm = to_bel(bc[k][:, R:R + N], N), to_bel(bc[k][:, R + N:R + 2 * N], N)
         if k == 1:
             uu, dd, Bm, Cm = uu.flip(-1), dd.flip(-1), Bm.flip(-1), Cm.flip(-1)

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--ops", default="scan,conv,norm,in_proj,out_proj,x_proj,dt_proj")
     ap.add_argument("--d", type=int, default=1024)
+    ap.add_argument("--delta-final", type=int, default=0)
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -70,7 +71,7 @@ def main():
         y = torch.empty(T, E, **bf)
         def f():
             rc = lib.pcad_op_biscan(ptr(u_f), ptr(dl_f), ptr(bc_f), ptr(u_r), ptr(dl_r), ptr(bc_r), RP, R, ptr(z), 2 * E,
-                                    ptr(A), ptr(Dp), ptr(bias), ptr(A2), ptr(Dp), ptr(bias), ptr(y), S, L, E, BF16, st)
+                                    ptr(A), ptr(Dp), ptr(bias), ptr(A2), ptr(Dp), ptr(bias), ptr(y), S, L, E, args.delta_final, BF16, st)
             assert rc == 0, lib.pcad_last_error(None)
         ms = timeit(f)
         out["scan_ms"] = ms
@@ -107,8 +108,12 @@ def main():
         Amat = rnd(T, lda)
         W = rnd(Nn, ldw, scale=K ** -0.5)
         Cm = torch.empty(T, ldc, **bf)
+        gbias = torch.full((Nn,), -4.0, device=dev)
         def f():
-            rc = lib.pcad_op_linear(ptr(Amat), ptr(W), ptr(Cm), T, Nn, K, lda, ldw, ldc, BF16, st)
+            if name == "dt_proj" and args.delta_final:
+                rc = lib.pcad_op_linear_softplus(ptr(Amat), ptr(W), ptr(gbias), ptr(Cm), T, Nn, K, lda, ldw, ldc, BF16, st)
+            else:
+                rc = lib.pcad_op_linear(ptr(Amat), ptr(W), ptr(Cm), T, Nn, K, lda, ldw, ldc, BF16, st)
             assert rc == 0, lib.pcad_last_error(None)
         ms = timeit(f)
         out[name + "_ms"] = ms
