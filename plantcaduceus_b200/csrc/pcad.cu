@@ -504,7 +504,7 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
     if (rc != PCAD_OK) break;
   }
   if (rc != PCAD_OK) {
-    snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
+    snprintf(g_create_error, sizeof(g_create_error), "%.511s", h->err);
     pcad_destroy(h);
     return PCAD_ERR_NOMEM;
   }
@@ -796,7 +796,7 @@ static pcad_handle* op_scratch() {
   return &scratch;
 }
 static int op_fail_to_global(int rc) {
-  if (rc != PCAD_OK) snprintf(g_create_error, sizeof(g_create_error), "%s", op_scratch()->err);
+  if (rc != PCAD_OK) snprintf(g_create_error, sizeof(g_create_error), "%.511s", op_scratch()->err);
   return rc;
 }
 static int op_num_sms() {

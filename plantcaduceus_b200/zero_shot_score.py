@@ -10,6 +10,8 @@ What changes is how the steps run:
   per-sequence HF tokenizer call in the main process     windows travel as ASCII bytes; tokenise + mask on the GPU
   model(input_ids).logits for all 512 x 8 positions      LM head only at the masked position, 4 columns
   Biopython / PyVCF3 / per-row Python loops              byte-level FASTA/VCF readers, vectorised numpy scoring
+  one process, one GPU                                   under torchrun: windows sharded over the ranks (one per GPU),
+                                                         per-variant scores gathered over NCCL, rank 0 writes
 
     python -m plantcaduceus_b200.zero_shot_score -input-table examples/example_snp.tsv -output out.tsv -model <dir|preset>
 """
@@ -175,10 +177,27 @@ def main(argv: Optional[Sequence[str]] = None):
         windows, recordIndices, header, records = seq_from_vcf(args)
         sequences = [bytes(r).decode("ascii") for r in windows]
 
-    model, tokenizer = load_model_and_tokenizer(args.model, args.device, args.dtype, args.seed)
+    # One process per GPU under torchrun: contiguous window ranges per rank, scores gathered to every rank
+    # (SURVEY.md 8e); a single process otherwise.
+    import torch
+
+    from . import sharding
+    rank, local_rank, world = sharding.env_world()
+    device = f"cuda:{local_rank}" if world > 1 else args.device
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        sharding.init_process_group(device=torch.device(device))
+    lo, hi = sharding.shard_range(len(sequences), rank, world)
+    model, tokenizer = load_model_and_tokenizer(args.model, device, args.dtype, args.seed)
     logging.info("Creating data loader")
-    loader = create_dataloader(sequences, tokenizer, args.batchSize, args.tokenIdx)
-    logits = extract_logits(model, loader, args.device, args.tokenIdx, tokenizer)
+    loader = create_dataloader(sequences[lo:hi], tokenizer, args.batchSize, args.tokenIdx)
+    logits = extract_logits(model, loader, device, args.tokenIdx, tokenizer)
+    if world > 1:
+        logits = sharding.gather_rows(torch.from_numpy(logits).to(device), len(sequences)).cpu().numpy()
+        torch.distributed.barrier()
+        if rank != 0:
+            torch.distributed.destroy_process_group()
+            return 0
 
     if args.inputDF is not None:
         snpDF["zeroShotScore"] = zero_shot_score(snpDF, logits)
@@ -193,6 +212,8 @@ def main(argv: Optional[Sequence[str]] = None):
     else:
         zero_shot_score_vcf(args, recordIndices, logits, header, records)
     logging.info(f"Zero-shot scores saved to {args.output}")
+    if world > 1:
+        torch.distributed.destroy_process_group()
     return 0
 
 
