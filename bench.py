@@ -127,6 +127,7 @@ def cpu_oracle_rate(model_name: str, n_windows: int, repeats: int = 1, warmup: i
     import torch
     from oracle import caduceus_oracle as O
     from plantcaduceus_b200 import preset, random_init_state_dict
+    torch.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core
     cfg = preset(model_name)
     sd = random_init_state_dict(cfg, seed=0)
     g = torch.Generator().manual_seed(seed)
@@ -162,7 +163,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "variants/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -315,13 +316,30 @@ def run_ours(args):
             "value": rate, "unit": "variants/s", "cores": threads, "kind": "port",
             "sample": f"{args.cpu_sample} window(s) of the same workload, fp32, oracle/caduceus_oracle.py "
                       f"({threads} torch threads of {os.cpu_count()} cpus), {ms / 1e3:.1f} s"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line on the real stdout (everything else -- NCCL banners, library chatter -- goes to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)          # fd 1 -> stderr for the duration of the run
     if args.impl == "reference":
         run_reference(args)
     else:
