@@ -42,13 +42,29 @@ struct GemmCfg {
 // which is dt_proj with the selective scan's delta_softplus / delta_bias step moved up into the GEMM
 // ([EXT] selective_scan_fn(..., delta_bias, delta_softplus=True)): the scan is bound by the MUFU pipe, this
 // write-bound GEMM has it idle.
-enum { kEpiPlain = 0, kEpiSoftplus = 1 };
+//
+// kEpiResidual / kEpiRowScale fold the block's fused residual-add RMSNorm ([EXT] rms_norm_fn(prenorm=True)) into the
+// two GEMMs around it, so the bf16 forward has no norm kernel between layers:
+//   out_proj, kEpiResidual:  r_new = acc + r_old (fp32), stored as the new residual stream (bf16), and
+//                            sumsq[row] += sum_cols r_new^2 (from the un-rounded fp32 sums, as the reference's stats);
+//   in_proj,  kEpiRowScale:  C = acc * rsqrt(sumsq[row] / K + eps), with the norm weight pre-multiplied into the
+//                            columns of W at load time: (r * rstd * w) W^T == rstd * (r (W diag(w))^T).
+enum { kEpiPlain = 0, kEpiSoftplus = 1, kEpiResidual = 2, kEpiRowScale = 3 };
+
+struct EpiParams {
+  const float* bias = nullptr;        // kEpiSoftplus: [N]
+  const bf16* resid = nullptr;        // kEpiResidual: [M, N] with row pitch ld_res (may alias C)
+  long long ld_res = 0;
+  float* sumsq_out = nullptr;         // kEpiResidual: [M], accumulated with atomicAdd (zeroed by the caller)
+  const float* sumsq_in = nullptr;    // kEpiRowScale: [M]
+  float inv_k = 0.f;                  // kEpiRowScale: 1 / (row length the sum of squares was taken over)
+  float eps = 0.f;
+};
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_c, long long M, int N, int K,
-                         const float* __restrict__ bias) {
+                         const __grid_constant__ CUtensorMap tmap_c, long long M, int N, int K, const EpiParams ep) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -152,6 +168,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccStride;
+      const long long grow = static_cast<long long>(m0) + q * 32 + lane;   // this lane's output row
+      const bool row_ok = grow < M;
+      float row_scale = 0.f, row_ss = 0.f;
+      if constexpr (EPI == kEpiRowScale) row_scale = row_ok ? rsqrtf(ep.sumsq_in[grow] * ep.inv_k + ep.eps) : 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 64) {
         if (n0 + c0 >= N) break;  // warp-uniform
@@ -160,15 +180,47 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         uint32_t r0[32], r1[32];
+        uint4 res[8];
+        if constexpr (EPI == kEpiResidual) {   // this row's 64 residual values: issued before the TMEM load returns
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = n0 + c0 + j * 8;
+            res[j] = (row_ok && col + 8 <= N) ? *reinterpret_cast<const uint4*>(ep.resid + grow * ep.ld_res + col)
+                                              : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         tmem_ld_32x32b_x32(t_row + c0, r0);
         if (c0 + 32 < BN) tmem_ld_32x32b_x32(t_row + c0 + 32, r1);
         tmem_ld_wait();
+        if constexpr (EPI == kEpiResidual) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t* r = (j < 4) ? (r0 + j * 8) : (r1 + (j - 4) * 8);
+            const uint32_t w[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
+            const bool col_ok = n0 + c0 + j * 8 + 8 <= N;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float v0 = __uint_as_float(r[2 * k]) + __uint_as_float(w[k] << 16);
+              const float v1 = __uint_as_float(r[2 * k + 1]) + __uint_as_float(w[k] & 0xffff0000u);
+              r[2 * k] = __float_as_uint(v0);
+              r[2 * k + 1] = __float_as_uint(v1);
+              if (col_ok) row_ss = fmaf(v0, v0, fmaf(v1, v1, row_ss));
+            }
+          }
+        }
+        if constexpr (EPI == kEpiRowScale) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            r0[k] = __float_as_uint(__uint_as_float(r0[k]) * row_scale);
+            r1[k] = __float_as_uint(__uint_as_float(r1[k]) * row_scale);
+          }
+        }
         if constexpr (EPI == kEpiSoftplus) {
 #pragma unroll
           for (int g = 0; g < 16; ++g) {
             const int col = n0 + c0 + g * 4;
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col + 4 <= N) b4 = *reinterpret_cast<const float4*>(bias + col);   // N % 4 == 0 is checked by the host
+            if (col + 4 <= N) b4 = *reinterpret_cast<const float4*>(ep.bias + col);   // N % 4 == 0 is checked by the host
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
             uint32_t* r = (g < 8) ? (r0 + g * 4) : (r1 + (g - 8) * 4);
 #pragma unroll
@@ -197,6 +249,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
+      if constexpr (EPI == kEpiResidual) {
+        if (row_ok) atomicAdd(ep.sumsq_out + grow, row_ss);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_read<0>();
@@ -257,7 +312,7 @@ inline int pick_bn(int N) {
 
 template <int BN, int EPI>
 inline cudaError_t launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, long long M, int N,
-                                  int K, const float* bias, int num_sms, cudaStream_t stream) {
+                                  int K, const EpiParams& ep, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -268,15 +323,14 @@ inline cudaError_t launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, 
   }
   const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
-  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, bias);
+  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, ep);
   return cudaGetLastError();
 }
 
-// Returns cudaSuccess or an error; *why is set for non-CUDA failures.  bias != nullptr selects the softplus
-// epilogue: C = softplus(A W^T + bias).
+// Returns cudaSuccess or an error; *why is set for non-CUDA failures.  `epi` selects the epilogue (EpiParams).
 inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long long M, int N, int K, long long lda,
                                      long long ldw, long long ldc, int num_sms, cudaStream_t stream,
-                                     const char** why, const float* bias = nullptr) {
+                                     const char** why, int epi = kEpiPlain, const EpiParams& ep = EpiParams()) {
   *why = nullptr;
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   if ((lda % 8) || (ldw % 8) || (ldc % 8) || (reinterpret_cast<uintptr_t>(A) & 15) ||
@@ -284,8 +338,17 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
     *why = "gemm: pointers must be 16-byte aligned and row pitches multiples of 8 elements";
     return cudaErrorInvalidValue;
   }
-  if (bias && ((N % 4) || (reinterpret_cast<uintptr_t>(bias) & 15))) {
-    *why = "gemm: the softplus epilogue needs N % 4 == 0 and a 16-byte aligned bias";
+  if (epi == kEpiSoftplus && (!ep.bias || (N % 4) || (reinterpret_cast<uintptr_t>(ep.bias) & 15))) {
+    *why = "gemm: the softplus epilogue needs a 16-byte aligned bias and N % 4 == 0";
+    return cudaErrorInvalidValue;
+  }
+  if (epi == kEpiResidual && (!ep.resid || !ep.sumsq_out || (N % 8) || (ep.ld_res % 8) ||
+                              (reinterpret_cast<uintptr_t>(ep.resid) & 15))) {
+    *why = "gemm: the residual epilogue needs resid (16-byte aligned, pitch % 8 == 0), sumsq_out and N % 8 == 0";
+    return cudaErrorInvalidValue;
+  }
+  if (epi == kEpiRowScale && !ep.sumsq_in) {
+    *why = "gemm: the row-scale epilogue needs sumsq_in";
     return cudaErrorInvalidValue;
   }
   const int BN = pick_bn(N);
@@ -295,20 +358,21 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
     *why = "gemm: cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
   }
-#define PCAD_GEMM_CASE(BNV)                                                                                      \
-  case BNV:                                                                                                      \
-    return bias ? launch_gemm_bn<BNV, kEpiSoftplus>(ta, tb, tc, M, N, K, bias, num_sms, stream)                  \
-                : launch_gemm_bn<BNV, kEpiPlain>(ta, tb, tc, M, N, K, nullptr, num_sms, stream);
-  switch (BN) {
-    PCAD_GEMM_CASE(64)
-    PCAD_GEMM_CASE(80)
-    PCAD_GEMM_CASE(96)
-    PCAD_GEMM_CASE(128)
-    default:
-      return bias ? launch_gemm_bn<256, kEpiSoftplus>(ta, tb, tc, M, N, K, bias, num_sms, stream)
-                  : launch_gemm_bn<256, kEpiPlain>(ta, tb, tc, M, N, K, nullptr, num_sms, stream);
+#define PCAD_GEMM_EPI(BNV)                                                                                  \
+  switch (epi) {                                                                                            \
+    case kEpiSoftplus: return launch_gemm_bn<BNV, kEpiSoftplus>(ta, tb, tc, M, N, K, ep, num_sms, stream);  \
+    case kEpiResidual: return launch_gemm_bn<BNV, kEpiResidual>(ta, tb, tc, M, N, K, ep, num_sms, stream);  \
+    case kEpiRowScale: return launch_gemm_bn<BNV, kEpiRowScale>(ta, tb, tc, M, N, K, ep, num_sms, stream);  \
+    default: return launch_gemm_bn<BNV, kEpiPlain>(ta, tb, tc, M, N, K, ep, num_sms, stream);               \
   }
-#undef PCAD_GEMM_CASE
+  switch (BN) {
+    case 64: PCAD_GEMM_EPI(64)
+    case 80: PCAD_GEMM_EPI(80)
+    case 96: PCAD_GEMM_EPI(96)
+    case 128: PCAD_GEMM_EPI(128)
+    default: PCAD_GEMM_EPI(256)
+  }
+#undef PCAD_GEMM_EPI
 }
 
 }  // namespace pcad

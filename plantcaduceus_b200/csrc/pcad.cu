@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -35,6 +36,7 @@ struct DirWeights {
 
 struct LayerWeights {
   void* in_proj = nullptr;   // [2E, d] act dtype
+  void* in_proj_s = nullptr; // [2E, d] bf16, columns pre-multiplied by norm_w (fused-norm path only)
   void* out_proj = nullptr;  // [d, E] act dtype
   float* norm_w = nullptr;   // [d]
   DirWeights dir[2];
@@ -54,6 +56,7 @@ struct Workspace {
   void* dbc[2] = {nullptr, nullptr};    // [T, RP]
   void* delta[2] = {nullptr, nullptr};  // [T, E]
   void* y = nullptr;           // [T, E]
+  float* sumsq[2] = {nullptr, nullptr};  // [T] row sums of squares of the residual stream (fused-norm path)
   uint8_t* ascii = nullptr;    // [B, L] staging for the host entry
   float* logits4 = nullptr;    // [B, 4] staging for the host entry
   int* pos = nullptr;          // [B] staging for the host entry
@@ -67,6 +70,7 @@ struct pcad_handle {
   int num_sms = 148;
   int d = 0, E = 0, N = 16, R = 0, RP = 0, V = 8;
   bool f32 = false;
+  bool fuse_norm = false;   // bf16 activations + bf16 residual: add+RMSNorm folded into the out_proj / in_proj epilogues
   size_t act_size = 2;
   bool finalized = false;
   char err[512] = "";
@@ -132,6 +136,28 @@ __global__ void convert_kernel(const SrcT* __restrict__ src, DstT* __restrict__ 
 __global__ void half_to_float_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __half2float(src[i]);
+}
+// W'[j, k] = W[j, k] * w[k]  (norm weight folded into in_proj's columns; fused-norm path)
+__global__ void scale_columns_kernel(const bf16* __restrict__ W, const float* __restrict__ w, bf16* __restrict__ out,
+                                     long long rows, int cols) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  out[i] = __float2bfloat16_rn(__bfloat162float(W[i]) * w[i % cols]);
+}
+// ss[row] = sum_j x[row, j]^2, one warp per row (layer 0 of the fused-norm path: the embedding output)
+__global__ void row_sumsq_kernel(const bf16* __restrict__ x, float* __restrict__ ss, long long rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float acc = 0.f;
+  for (int j = lane * 8; j < d; j += 256) {
+    float v[8];
+    load16<bf16>(x + row * d + j, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(v[k], v[k], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) ss[row] = acc;
 }
 __global__ void neg_exp_kernel(float* __restrict__ a, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -207,13 +233,14 @@ struct StageTimer {
 
 // ---- operator launchers (shared by the forward pass and the pcad_op_* entry points) -------------
 int op_linear(pcad_handle* h, const void* A, const void* W, void* C, long long M, int N, int K, long long lda,
-              long long ldw, long long ldc, bool f32, int num_sms, cudaStream_t st, const float* softplus_bias = nullptr) {
+              long long ldw, long long ldc, bool f32, int num_sms, cudaStream_t st, int epi = kEpiPlain,
+              const EpiParams& ep = EpiParams()) {
   if (f32) {
-    if (softplus_bias) return fail(h, PCAD_ERR_INVALID, "the softplus epilogue exists for bf16 only");
+    if (epi != kEpiPlain) return fail(h, PCAD_ERR_INVALID, "fused GEMM epilogues exist for bf16 only");
     CUDA_TRY(h, gemm_f32_simt(static_cast<const float*>(A), static_cast<const float*>(W), static_cast<float*>(C), M, N, K, lda, ldw, ldc, st));
   } else {
     const char* why = nullptr;
-    cudaError_t e = gemm_bf16_tcgen05(static_cast<const bf16*>(A), static_cast<const bf16*>(W), static_cast<bf16*>(C), M, N, K, lda, ldw, ldc, num_sms, st, &why, softplus_bias);
+    cudaError_t e = gemm_bf16_tcgen05(static_cast<const bf16*>(A), static_cast<const bf16*>(W), static_cast<bf16*>(C), M, N, K, lda, ldw, ldc, num_sms, st, &why, epi, ep);
     if (e != cudaSuccess) return fail(h, why ? PCAD_ERR_INVALID : PCAD_ERR_CUDA, "%s", why ? why : cudaGetErrorString(e));
   }
   return PCAD_OK;
@@ -298,6 +325,7 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
   const size_t o_dbc0 = take(T * h->RP * a), o_dbc1 = take(T * h->RP * a);
   const size_t o_dl0 = take(T * h->E * a), o_dl1 = take(T * h->E * a);
   const size_t o_y = take(T * h->E * a);
+  const size_t o_ss0 = take(T * sizeof(float)), o_ss1 = take(T * sizeof(float));
   const size_t o_ascii = take(static_cast<size_t>(B) * L);
   const size_t o_l4 = take(static_cast<size_t>(B) * 4 * sizeof(float));
   const size_t o_pos = take(static_cast<size_t>(B) * sizeof(int));
@@ -306,6 +334,7 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
     ws->ids = p + o_ids; ws->hid = p + o_hid; ws->resid = p + o_res; ws->normed = p + o_nrm; ws->xz = p + o_xz;
     ws->xc[0] = p + o_xc0; ws->xc[1] = p + o_xc1; ws->dbc[0] = p + o_dbc0; ws->dbc[1] = p + o_dbc1;
     ws->delta[0] = p + o_dl0; ws->delta[1] = p + o_dl1; ws->y = p + o_y;
+    ws->sumsq[0] = reinterpret_cast<float*>(p + o_ss0); ws->sumsq[1] = reinterpret_cast<float*>(p + o_ss1);
     ws->ascii = p + o_ascii; ws->logits4 = reinterpret_cast<float*>(p + o_l4); ws->pos = reinterpret_cast<int*>(p + o_pos);
   }
   return off;
@@ -336,25 +365,39 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
   const int d = h->d, E = h->E, R = h->R, RP = h->RP;
   const bool f32 = h->f32;
   const bool res_f32 = f32 || h->cfg.residual_in_fp32;
+  const bool fused = h->fuse_norm;
+  // Fused-norm path (bf16 activations, bf16 residual): the residual stream lives in ws.resid, its row sums of
+  // squares in ws.sumsq[cur]; out_proj's epilogue adds into it, in_proj's epilogue applies rstd.  Otherwise the
+  // block is norm kernel -> in_proj ... out_proj -> ws.hid, exactly the reference's order of roundings.
+  int cur = 0;
   {
-    StageTimer tm(h, st, PCAD_ST_EMBED);
+    StageTimer tm(h, st, PCAD_ST_EMBED, fused ? 2 : 1);
     const long long total = T * (d / 8);
     const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
     if (f32) embed_kernel<float><<<blocks, 256, 0, st>>>(ws.ids, static_cast<const float*>(h->emb), static_cast<float*>(ws.hid), B, L, d, h->comp_dev);
-    else embed_kernel<bf16><<<blocks, 256, 0, st>>>(ws.ids, static_cast<const bf16*>(h->emb), static_cast<bf16*>(ws.hid), B, L, d, h->comp_dev);
+    else embed_kernel<bf16><<<blocks, 256, 0, st>>>(ws.ids, static_cast<const bf16*>(h->emb), static_cast<bf16*>(fused ? ws.resid : ws.hid), B, L, d, h->comp_dev);
+    if (fused) row_sumsq_kernel<<<static_cast<unsigned>((T + 7) / 8), 256, 0, st>>>(static_cast<const bf16*>(ws.resid), ws.sumsq[cur], T, d);
     CUDA_TRY(h, cudaGetLastError());
   }
   for (int li = 0; li < h->cfg.n_layer; ++li) {
     LayerWeights& lw = h->layers[li];
     int rc;
-    {
+    if (!fused) {
       StageTimer tm(h, st, PCAD_ST_NORM);
       rc = op_add_rmsnorm(h, ws.hid, li == 0 ? nullptr : ws.resid, lw.norm_w, ws.normed, ws.resid, T, d, h->cfg.norm_eps, f32, res_f32, st);
       if (rc) return rc;
     }
     {
       StageTimer tm(h, st, PCAD_ST_IN_PROJ);
-      rc = op_linear(h, ws.normed, lw.in_proj, ws.xz, T, 2 * E, d, d, d, 2 * E, f32, h->num_sms, st);
+      if (fused) {
+        EpiParams ep;
+        ep.sumsq_in = ws.sumsq[cur];
+        ep.inv_k = 1.0f / static_cast<float>(d);
+        ep.eps = h->cfg.norm_eps;
+        rc = op_linear(h, ws.resid, lw.in_proj_s, ws.xz, T, 2 * E, d, d, d, 2 * E, false, h->num_sms, st, kEpiRowScale, ep);
+      } else {
+        rc = op_linear(h, ws.normed, lw.in_proj, ws.xz, T, 2 * E, d, d, d, 2 * E, f32, h->num_sms, st);
+      }
       if (rc) return rc;
     }
     {
@@ -387,13 +430,25 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
     }
     {
       StageTimer tm(h, st, PCAD_ST_OUT_PROJ);
-      rc = op_linear(h, ws.y, lw.out_proj, ws.hid, T, d, E, E, E, d, f32, h->num_sms, st);
+      if (fused) {
+        CUDA_TRY(h, cudaMemsetAsync(ws.sumsq[cur ^ 1], 0, static_cast<size_t>(T) * sizeof(float), st));
+        EpiParams ep;
+        ep.resid = static_cast<const bf16*>(ws.resid);
+        ep.ld_res = d;
+        ep.sumsq_out = ws.sumsq[cur ^ 1];
+        rc = op_linear(h, ws.y, lw.out_proj, ws.resid, T, d, E, E, E, d, false, h->num_sms, st, kEpiResidual, ep);
+        cur ^= 1;
+      } else {
+        rc = op_linear(h, ws.y, lw.out_proj, ws.hid, T, d, E, E, E, d, f32, h->num_sms, st);
+      }
       if (rc) return rc;
     }
   }
   {
     StageTimer tm(h, st, PCAD_ST_NORM);
-    int rc = op_add_rmsnorm(h, ws.hid, h->cfg.n_layer == 0 ? nullptr : ws.resid, h->norm_f, ws.normed, nullptr, T, d, h->cfg.norm_eps, f32, res_f32, st);
+    int rc;
+    if (fused) rc = op_add_rmsnorm(h, ws.resid, nullptr, h->norm_f, ws.normed, nullptr, T, d, h->cfg.norm_eps, false, false, st);
+    else rc = op_add_rmsnorm(h, ws.hid, h->cfg.n_layer == 0 ? nullptr : ws.resid, h->norm_f, ws.normed, nullptr, T, d, h->cfg.norm_eps, f32, res_f32, st);
     if (rc) return rc;
   }
   return PCAD_OK;
@@ -473,6 +528,8 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   h->V = cfg->vocab_size;
   h->f32 = cfg->dtype == PCAD_F32;
   h->act_size = h->f32 ? 4 : 2;
+  h->fuse_norm = !h->f32 && !cfg->residual_in_fp32;
+  if (const char* nf = getenv("PCAD_NO_FUSED_NORM")) { if (nf[0] == '1') h->fuse_norm = false; }   // A/B switch for tests
   memset(h->prof_ms, 0, sizeof(h->prof_ms));
   memset(h->prof_launches, 0, sizeof(h->prof_launches));
   h->layers.resize(cfg->n_layer);
@@ -488,6 +545,7 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   rc |= dev_alloc(h, &h->bad_flag, 1);
   for (auto& lw : h->layers) {
     rc |= A8(&lw.in_proj, static_cast<size_t>(2) * h->E * h->d * a);
+    if (h->fuse_norm) rc |= A8(&lw.in_proj_s, static_cast<size_t>(2) * h->E * h->d * a);
     rc |= A8(&lw.out_proj, static_cast<size_t>(h->d) * h->E * a);
     rc |= dev_alloc(h, &lw.norm_w, h->d);
     for (int dir = 0; dir < 2; ++dir) {
@@ -666,6 +724,14 @@ int pcad_finalize(pcad_handle* h) {
       for (int k = 0; k < 7; ++k)
         if (!lw.dir[dir].has[k]) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d mamba_%s.%s", li, dir ? "rev" : "fwd", names[k]);
   }
+  if (h->fuse_norm) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long rows = 2LL * h->E, n = rows * h->d;
+    for (auto& lw : h->layers)
+      scale_columns_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(static_cast<const bf16*>(lw.in_proj), lw.norm_w,
+                                                                           static_cast<bf16*>(lw.in_proj_s), rows, h->d);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+  }
   h->finalized = true;
   return PCAD_OK;
 }
@@ -813,7 +879,29 @@ int pcad_op_linear(const void* A, const void* W, void* C, int64_t M, int N, int 
 
 int pcad_op_linear_softplus(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream) {
   if (dtype != PCAD_BF16 || !bias) return PCAD_ERR_INVALID;
-  return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), bias));
+  EpiParams ep;
+  ep.bias = bias;
+  return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiSoftplus, ep));
+}
+
+int pcad_op_linear_residual(const void* A, const void* W, const void* resid_in, void* resid_out, float* sumsq_out, int64_t M, int N, int K,
+                            int64_t lda, int64_t ldw, int64_t ld_res, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 || !resid_in || !sumsq_out) return PCAD_ERR_INVALID;
+  EpiParams ep;
+  ep.resid = static_cast<const bf16*>(resid_in);
+  ep.ld_res = ld_res;
+  ep.sumsq_out = sumsq_out;
+  return op_fail_to_global(op_linear(op_scratch(), A, W, resid_out, M, N, K, lda, ldw, ld_res, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiResidual, ep));
+}
+
+int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in, float eps, void* C, int64_t M, int N, int K,
+                            int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 || !sumsq_in) return PCAD_ERR_INVALID;
+  EpiParams ep;
+  ep.sumsq_in = sumsq_in;
+  ep.inv_k = 1.0f / static_cast<float>(K);
+  ep.eps = eps;
+  return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiRowScale, ep));
 }
 
 int pcad_op_add_rmsnorm(const void* x, const void* res_in, const float* w, void* y, void* res_out, int64_t rows, int d, float eps, int dtype, int res_dtype, void* stream) {

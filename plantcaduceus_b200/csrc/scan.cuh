@@ -28,7 +28,10 @@
 
 namespace pcad {
 
-constexpr int kScanTC = 16;      // timesteps per chunk
+#ifndef PCAD_SCAN_TC
+#define PCAD_SCAN_TC 16
+#endif
+constexpr int kScanTC = PCAD_SCAN_TC;      // timesteps per chunk
 constexpr int kScanCH = 128;     // channels per CTA
 constexpr int kScanThreads = 2 * kScanCH;
 constexpr int kScanN = 16;       // d_state

@@ -104,6 +104,25 @@ def test_l20_fp32_and_bf16_real_shape(Model, cuda_device):
     assert_bf16_parity(got16, want, want16, scored=(slice(None), 255, slice(3, 7)))
 
 
+def test_bf16_fused_norm_matches_unfused(Model, cuda_device, monkeypatch):
+    """The bf16 forward folds add+RMSNorm into the out_proj / in_proj epilogues; PCAD_NO_FUSED_NORM=1 runs the
+    separate norm kernel instead.  Both must sit at the same distance from the fp32 oracle."""
+    cfg = CaduceusConfig(d_model=256, n_layer=4)
+    sd = random_init_state_dict(cfg, seed=8)
+    ids = make_ids(3, 200, seed=2, mask_at=100)
+    want, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    fused = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    a = fused(input_ids=ids.to(cuda_device)).logits.cpu()
+    monkeypatch.setenv("PCAD_NO_FUSED_NORM", "1")
+    unfused = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    b = unfused(input_ids=ids.to(cuda_device)).logits.cpu()
+    assert fused.launch_count() < unfused.launch_count()
+    ea, eb = (a - want).abs().max().item(), (b - want).abs().max().item()
+    print(f"fused {ea:.4g}  unfused {eb:.4g}")
+    assert ea <= max(2e-2, 1.5 * eb)
+    assert (a - b).abs().max().item() <= 2e-2
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_engine_rc_equivariance(Model, cuda_device, dtype):
     """Size-independent property: logits(RC(ids)) == logits(ids).flip(L)[..., comp]."""

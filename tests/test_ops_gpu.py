@@ -66,6 +66,39 @@ def test_linear_softplus_epilogue(lib, cuda_device, M, N, K, lda):
     assert torch.allclose(got, want, rtol=2 ** -7, atol=1e-6)
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 1024, 2048), (300, 384, 768), (128, 128, 64), (77, 256, 256)])
+def test_linear_residual_and_rowscale_epilogues(lib, cuda_device, M, N, K):
+    """out_proj with the residual add + row sum of squares, and in_proj with the RMSNorm row scale, == the separate
+    add+RMSNorm followed by the GEMM (up to where the bf16 roundings sit)."""
+    g = torch.Generator().manual_seed(M * 3 + N)
+    A = torch.randn(M, K, generator=g).to(cuda_device, torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device, torch.bfloat16)
+    resid = torch.randn(M, N, generator=g).to(cuda_device, torch.bfloat16)
+    resid_io = resid.clone()
+    sumsq = torch.zeros(M, device=cuda_device)
+    check(lib, lib.pcad_op_linear_residual(ptr(A), ptr(W), ptr(resid_io), ptr(resid_io), ptr(sumsq), M, N, K, K, K, N, BF16, stream()))
+    torch.cuda.synchronize()
+    want = A.float() @ W.float().t() + resid.float()
+    assert (resid_io.float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-3
+    want_ss = want.pow(2).sum(-1)
+    assert torch.allclose(sumsq, want_ss, rtol=1e-4, atol=1e-3)
+    # row scale: C = (X Wn^T) * rsqrt(mean(X^2) + eps), sums of squares taken from above
+    d = N
+    X = resid_io                                   # [M, d] plays the residual stream
+    w_norm = (1 + 0.1 * torch.randn(d, generator=g)).to(cuda_device)
+    W2 = (torch.randn(2 * d, d, generator=g) / d ** 0.5).to(cuda_device, torch.bfloat16)
+    W2s = (W2.float() * w_norm[None, :]).to(torch.bfloat16)
+    out = torch.full((M, 2 * d), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    eps = 1e-5
+    check(lib, lib.pcad_op_linear_rowscale(ptr(X), ptr(W2s), ptr(sumsq), C.c_float(eps), ptr(out), M, 2 * d, d, d, d, 2 * d, BF16, stream()))
+    torch.cuda.synchronize()
+    normed = (want * torch.rsqrt(want.pow(2).mean(-1, keepdim=True) + eps) * w_norm[None, :])
+    ref = normed @ W2.float().t()
+    err = (out.float() - ref).abs().max().item()
+    assert not torch.isnan(out.float()).any()
+    assert err <= 2 ** -6 * ref.abs().max().item() + 2e-3, err
+
+
 def test_linear_bf16_strided(lib, cuda_device):
     """A taken as the first K columns of a wider matrix (dt_proj reads dt out of [T, R+2N])."""
     M, N, K, lda = 512, 768, 24, 64
