@@ -17,8 +17,10 @@
 //
 // The bf16 kernel is bound by the MUFU (ex2) and FMA pipes, not by HBM (ncu: profiles/).  Its inner loop
 // (a) keeps (n, n+1) state pairs in 64-bit registers and uses the packed fp32x2 instructions of sm_100
-// (FFMA2 / FMUL2: two lanes per issue slot), (b) takes kScanPoly of the 8 pair-exponentials from an FMA-pipe
-// polynomial instead of MUFU.EX2, (c) works in the log2 domain end to end: d' = log2(1 + 2^((delta + bias) log2 e)),
+// (FFMA2 / FMUL2: two lanes per issue slot), (b) can take kScanPoly of the 8 pair-exponentials from an FMA-pipe
+// polynomial instead of MUFU.EX2 (default 0: measured on B200 at l32, B = 256: 0 -> 5.56 ms, 1 -> 5.57, 2 -> 5.91,
+// 3 -> 6.34 per launch -- a polynomial exp costs as many FMA-pipe cycles as the MUFU cycles it saves and the two
+// pipes share issue slots), (c) works in the log2 domain end to end: d' = log2(1 + 2^((delta + bias) log2 e)),
 // exp(d A) = 2^(d' A), and the ln 2 that d = d' ln 2 owes to the input term is folded into B when B is converted.
 #pragma once
 
@@ -36,7 +38,7 @@ constexpr int kScanCH = 128;     // channels per CTA
 constexpr int kScanThreads = 2 * kScanCH;
 constexpr int kScanN = 16;       // d_state
 #ifndef PCAD_SCAN_POLY
-#define PCAD_SCAN_POLY 1
+#define PCAD_SCAN_POLY 0
 #endif
 constexpr int kScanPoly = PCAD_SCAN_POLY;   // pairs (of 8) whose exp2 runs on the FMA pipe
 #ifndef PCAD_SCAN_MINBLOCKS
