@@ -18,23 +18,27 @@ namespace pcad {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;  // 64 bf16 = 128 bytes = one swizzle row
-constexpr int kGemmThreads = 192;
 
-template <int BN>
+// EW = number of epilogue warps: 4 (one per TMEM lane quarter), or 8 (two per quarter, alternating 64-column
+// chunks) for epilogues that do real math per element (softplus) -- with one warp per scheduler that math is
+// latency-bound.  The EW = 8 configuration keeps only 2 ring stages (it is used with K <= 64, one k-block per tile)
+// so that the 8 x 2 staging slabs fit.
+template <int BN, int EW>
 struct GemmCfg {
+  static constexpr int kThreads = 64 + 32 * EW;
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
   static constexpr int kBBytes = BN * kGemmBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // B tiles must keep 1024-byte alignment inside the ring: pad each B slot to a multiple of 1024.
   static constexpr int kBSlot = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kSlot = kABytes + kBSlot;
-  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kStages = (EW == 8) ? 2 : ((BN >= 256) ? 4 : 6);
   static constexpr int kAccStride = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kBarBytes = 256;
-  // epilogue staging: 4 warps x 2 buffers x (32 rows x 64 bf16 = 4 KB), each slab 1024-byte aligned
+  // epilogue staging: EW warps x 2 buffers x (32 rows x 64 bf16 = 4 KB), each slab 1024-byte aligned
   static constexpr int kEpiSlab = 32 * 64 * 2;
-  static constexpr int kEpiBytes = 4 * 2 * kEpiSlab;
+  static constexpr int kEpiBytes = EW * 2 * kEpiSlab;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kSlot + kEpiBytes + kBarBytes;
 };
 
@@ -61,11 +65,11 @@ struct EpiParams {
   float eps = 0.f;
 };
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int EPI, int EW>
+__global__ void __launch_bounds__(GemmCfg<BN, EW>::kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, long long M, int N, int K, const EpiParams ep) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,7 +98,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], 32 * EW);
     }
     fence_mbar_init();
   }
@@ -156,9 +160,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else {
-    // epilogue warps 2..5; TMEM lane quarter is fixed by warp id % 4
+    // epilogue warps 2..(2+EW); TMEM lane quarter is fixed by warp id % 4; with EW = 8 the two warps of a quarter
+    // take alternate 64-column chunks
     const int q = warp & 3;
-    uint8_t* slab = epi + q * 2 * Cfg::kEpiSlab;
+    const int ew = warp - 2;
+    constexpr int kChunkStep = 64 * (EW / 4);
+    uint8_t* slab = epi + ew * 2 * Cfg::kEpiSlab;
     int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -173,7 +180,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       float row_scale = 0.f, row_ss = 0.f;
       if constexpr (EPI == kEpiRowScale) row_scale = row_ok ? rsqrtf(ep.sumsq_in[grow] * ep.inv_k + ep.eps) : 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {
+      for (int c0 = (ew >> 2) * 64; c0 < BN; c0 += kChunkStep) {
         if (n0 + c0 >= N) break;  // warp-uniform
         uint8_t* dst = slab + buf * Cfg::kEpiSlab;
         // the TMA store that read this buffer two chunks ago must have drained it
@@ -310,20 +317,20 @@ inline int pick_bn(int N) {
   return waste128 < waste256 ? 128 : 256;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int EW = 4>
 inline cudaError_t launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, long long M, int N,
                                   int K, const EpiParams& ep, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
-  gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, ep);
+  gemm_bf16_tcgen05_kernel<BN, EPI, EW><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, ep);
   return cudaGetLastError();
 }
 
@@ -360,7 +367,7 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
   }
 #define PCAD_GEMM_EPI(BNV)                                                                                  \
   switch (epi) {                                                                                            \
-    case kEpiSoftplus: return launch_gemm_bn<BNV, kEpiSoftplus>(ta, tb, tc, M, N, K, ep, num_sms, stream);  \
+    case kEpiSoftplus: return launch_gemm_bn<BNV, kEpiSoftplus, 8>(ta, tb, tc, M, N, K, ep, num_sms, stream); \
     case kEpiResidual: return launch_gemm_bn<BNV, kEpiResidual>(ta, tb, tc, M, N, K, ep, num_sms, stream);  \
     case kEpiRowScale: return launch_gemm_bn<BNV, kEpiRowScale>(ta, tb, tc, M, N, K, ep, num_sms, stream);  \
     default: return launch_gemm_bn<BNV, kEpiPlain>(ta, tb, tc, M, N, K, ep, num_sms, stream);               \

@@ -70,6 +70,7 @@ struct pcad_handle {
   int num_sms = 148;
   int d = 0, E = 0, N = 16, R = 0, RP = 0, V = 8;
   bool f32 = false;
+  bool dt_softplus_epilogue = false;   // bf16: softplus(dt_proj + bias) in the GEMM epilogue, scan takes delta as is
   bool fuse_norm = false;   // bf16 activations + bf16 residual: add+RMSNorm folded into the out_proj / in_proj epilogues
   size_t act_size = 2;
   bool finalized = false;
@@ -413,10 +414,15 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
       }
       {
         StageTimer tm(h, st, PCAD_ST_DT_PROJ);
-        // The softplus(dt_proj + bias) GEMM epilogue (pcad_op_linear_softplus + delta_final scan) was measured
-        // slower end to end on B200 (dt_proj 0.21 -> 0.50 ms, scan 5.57 -> 5.42 ms per l32 layer at B = 256), so
-        // the forward keeps the reference's order: raw dt_proj output, softplus inside the scan.
-        rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, f32, h->num_sms, st);
+        // Optional (bf16): softplus(dt_proj + bias) in the GEMM epilogue (8 epilogue warps) so the MUFU-bound scan gets
+        // delta ready-made (delta_final).  Default and fp32: the reference's order (raw dt_proj, softplus in the scan).
+        if (h->dt_softplus_epilogue) {
+          EpiParams ep;
+          ep.bias = lw.dir[dir].dt_bias;
+          rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, false, h->num_sms, st, kEpiSoftplus, ep);
+        } else {
+          rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, f32, h->num_sms, st);
+        }
         if (rc) return rc;
       }
     }
@@ -425,7 +431,7 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
       const uint8_t* zbase = static_cast<const uint8_t*>(ws.xz) + static_cast<size_t>(E) * h->act_size;
       rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
                      lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
-                     /*delta_final=*/false, st);
+                     /*delta_final=*/h->dt_softplus_epilogue, st);
       if (rc) return rc;
     }
     {
@@ -529,6 +535,10 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   h->f32 = cfg->dtype == PCAD_F32;
   h->act_size = h->f32 ? 4 : 2;
   h->fuse_norm = !h->f32 && !cfg->residual_in_fp32;
+  // Off by default: measured zero-sum on B200 (l32, B = 256: scan -11.5 ms, dt_proj +12.3 ms per step), so the
+  // forward keeps the reference's order of operations; PCAD_DT_SOFTPLUS_EPILOGUE=1 switches it on for experiments.
+  h->dt_softplus_epilogue = false;
+  if (const char* ds = getenv("PCAD_DT_SOFTPLUS_EPILOGUE")) h->dt_softplus_epilogue = !h->f32 && ds[0] == '1';
   if (const char* nf = getenv("PCAD_NO_FUSED_NORM")) { if (nf[0] == '1') h->fuse_norm = false; }   // A/B switch for tests
   memset(h->prof_ms, 0, sizeof(h->prof_ms));
   memset(h->prof_launches, 0, sizeof(h->prof_launches));
