@@ -38,6 +38,8 @@ if ROOT not in sys.path:
 # Algorithmic work per 512-bp window; bf16 activations.
 SCAN_MB_PER_WINDOW = {"l20": 193.3, "l24": 308.3, "l28": 537.7, "l32": 817.9}
 GEMM_GFLOP_PER_WINDOW = {"l20": 41.27, "l24": 86.97, "l28": 225.49, "l32": 455.27}
+# exponentials in the scan per window (one per state update; l32 2.147 G) -- the pipe that actually binds
+SCAN_GEXP_PER_WINDOW = {"l20": 0.503, "l24": 0.805, "l28": 1.409, "l32": 2.147}
 TOKEN_IDX = 255
 WINDOW = 512
 
@@ -275,6 +277,12 @@ def run_ours(args):
     scan_launch_ms = prof["scan"]["ms"] / max(1, prof["scan"]["launches"])
     scan_bytes_per_launch = SCAN_MB_PER_WINDOW[args.model] * 1e6 * B / cfg.n_layer
     scan_gbs = scan_bytes_per_launch / (scan_launch_ms * 1e-3) / 1e9
+    # MUFU view of the same kernel: 16 ex2 per (step, channel, direction) + 2 for softplus + 1 for the gate = 19/16 of
+    # the state-update count, against 16 MUFU lanes / clk / SM (measured: tools/ub/fma_pipes.cu) at the observed clock
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    mufu_peak = 16.0 * 148 * sm_mhz * 1e6
+    mufu_ops = SCAN_GEXP_PER_WINDOW[args.model] * 1e9 * B / cfg.n_layer * (19.0 / 16.0)
+    mufu_rate = mufu_ops / (scan_launch_ms * 1e-3)
     gemm_ms = stage_ms["in_proj"] + stage_ms["out_proj"] + stage_ms["x_proj"] + stage_ms["dt_proj"]
     gemm_tflops = GEMM_GFLOP_PER_WINDOW[args.model] * 1e9 * B / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
     traffic = None
@@ -302,6 +310,10 @@ def run_ours(args):
             "traffic": traffic, "peak_source": peaks["source"], "ms_per_launch": scan_launch_ms,
             "algorithmic_bytes_per_launch": scan_bytes_per_launch,
         },
+        "roofline_mufu": {
+            "kernel": "biscan_kernel", "bound": "mufu (ex2/lg2/rcp special-function pipe: what binds the scan at d_state 16)",
+            "achieved": mufu_rate / 1e12, "peak": mufu_peak / 1e12, "unit": "Tops/s", "frac": mufu_rate / mufu_peak,
+            "note": "19 MUFU ops per 16 state updates; peak = 16 lanes/clk/SM x 148 SMs x sampled SM clock"},
         "gemm": {"achieved_tflops": gemm_tflops, "peak_tflops": peaks["bf16"],
                  "frac": (gemm_tflops / peaks["bf16"]) if gemm_tflops else None,
                  "note": "minimal algorithmic FLOPs (in/out_proj once per strand) over the summed GEMM-stage time"},
