@@ -63,3 +63,56 @@ def test_long_context_hidden_states_match_oracle(cuda_device, L):
     want_emb = want_hs[-1][:, L // 2, :]
     want_avg = (want_emb[:, :d] + want_emb[:, d:].flip(-1)) / 2
     assert torch.allclose(avg, want_avg, rtol=1e-3, atol=1e-4)
+
+
+def test_zero_shot_eval_helpers_match_reference_formulas(cuda_device):
+    """`_masked_probs` (multi-mask, masked_select order), `_unmasked_probs` ([N, L, 4]) and `_sv_llr_boundary`
+    (reference src/zero-shot-eval.py:129-243) against the oracle / a literal restatement of the reference loop."""
+    from plantcaduceus_b200 import CharDNATokenizer
+    from plantcaduceus_b200 import zero_shot_eval as zse
+    from plantcaduceus_b200.modeling import CaduceusForMaskedLM
+    cfg = CaduceusConfig(d_model=128, n_layer=2)
+    sd = random_init_state_dict(cfg, seed=21)
+    tok = CharDNATokenizer()
+    rng = np.random.default_rng(5)
+    N, L = 5, 80
+    seqs = ["".join(rng.choice(list("ACGT"), size=L)) for _ in range(N)]
+    model = CaduceusForMaskedLM.from_pretrained(sd, config=cfg, torch_dtype=torch.float32).to(cuda_device)
+    mask_idx = [40, 7, 41]
+    got = zse.masked_probs(model, tok, seqs, mask_idx, batch_size=2)
+    ids = torch.from_numpy(tok.encode_bytes(tok.windows_to_ascii(seqs, L)).astype(np.int64))
+    masked = ids.clone()
+    masked[:, mask_idx] = tok.mask_token_id
+    lg, _ = O.caduceus_forward(sd, cfg, masked, dtype=torch.float32)
+    sel = torch.masked_select(lg, (masked == tok.mask_token_id).unsqueeze(-1).expand(-1, -1, 8)).view(-1, 8)
+    want = torch.softmax(sel[:, 3:7].float(), dim=-1).numpy()
+    assert got.shape == (N * 3, 4) and np.allclose(got, want, rtol=2e-4, atol=1e-6)
+    up = zse.unmasked_probs(model, tok, seqs, batch_size=3)
+    lg2, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    want_up = torch.softmax(lg2[..., 3:7].float(), dim=-1).numpy()
+    assert up.shape == (N, L, 4) and np.allclose(up, want_up, rtol=2e-4, atol=1e-6)
+    # boundary score: literal restatement of the reference's loop
+    flank = 3
+    left = rng.integers(10, 30, N)
+    right = left + rng.integers(5, 20, N)
+    mut = ["".join(rng.choice(list("ACGTN"), size=L)) for _ in range(N)]
+    mp = np.abs(rng.normal(size=(N, L, 4))).astype(np.float32) + 1e-3
+    mp /= mp.sum(-1, keepdims=True)
+    got_sv = zse.sv_llr_boundary(left, right, mut, up, mp, flank)
+    c0 = L // 2
+    want_sv = np.zeros(N)
+    for i in range(N):
+        le = int(left[i]) - 1
+        lref = list(range(le - (flank - 1), le + 1))
+        rref = list(range(int(right[i]) + 1, int(right[i]) + 1 + flank))
+        centre = mut[i][c0 - flank:c0 + flank]
+        vals = []
+        for k in range(flank):
+            for p_ref1, p_mut0, b in ((lref[k], c0 - flank + k, centre[k]), (rref[k], c0 + k, centre[flank + k])):
+                if b in "ACGT":
+                    j = "ACGT".index(b)
+                    vals.append(float(np.log(max(mp[i, p_mut0, j], 1e-12) / max(up[i, p_ref1 - 1, j], 1e-12))))
+                else:
+                    vals.append(0.0)
+        want_sv[i] = -float(np.mean(vals))
+    assert np.allclose(got_sv, want_sv, rtol=1e-5, atol=1e-7)
