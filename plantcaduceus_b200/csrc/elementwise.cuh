@@ -135,46 +135,51 @@ add_rmsnorm_kernel(const T* __restrict__ x, const RT* __restrict__ res_in, const
 constexpr int kConvTT = 64;   // timesteps per thread (halo re-read: 6 / 64)
 constexpr int kConvBlk = 8;   // rows fetched per batch of back-to-back loads
 
-template <typename T> struct Raw4;               // 4 channels as loaded from memory
-template <> struct Raw4<bf16> { typedef uint2 type; };
-template <> struct Raw4<float> { typedef float4 type; };
+// CPT channels per thread as loaded from memory
+template <typename T, int CPT> struct RawC;
+template <> struct RawC<bf16, 4> { typedef uint2 type; };
+template <> struct RawC<bf16, 2> { typedef uint32_t type; };
+template <> struct RawC<float, 4> { typedef float4 type; };
+template <> struct RawC<float, 2> { typedef float2 type; };
 
-template <typename T>
-__device__ __forceinline__ typename Raw4<T>::type load4_raw(const T* p) {
-  return *reinterpret_cast<const typename Raw4<T>::type*>(p);
-}
-__device__ __forceinline__ void cvt4(const uint2& raw, float (&v)[4]) {
+__device__ __forceinline__ void cvtc(const uint2& raw, float (&v)[4]) {
   v[0] = __uint_as_float(raw.x << 16); v[1] = __uint_as_float(raw.x & 0xffff0000u);
   v[2] = __uint_as_float(raw.y << 16); v[3] = __uint_as_float(raw.y & 0xffff0000u);
 }
-__device__ __forceinline__ void cvt4(const float4& raw, float (&v)[4]) {
-  v[0] = raw.x; v[1] = raw.y; v[2] = raw.z; v[3] = raw.w;
+__device__ __forceinline__ void cvtc(const uint32_t& raw, float (&v)[2]) {
+  v[0] = __uint_as_float(raw << 16); v[1] = __uint_as_float(raw & 0xffff0000u);
 }
-template <typename T>
-__device__ __forceinline__ void store4(T* p, const float (&v)[4]) {
+__device__ __forceinline__ void cvtc(const float4& raw, float (&v)[4]) { v[0] = raw.x; v[1] = raw.y; v[2] = raw.z; v[3] = raw.w; }
+__device__ __forceinline__ void cvtc(const float2& raw, float (&v)[2]) { v[0] = raw.x; v[1] = raw.y; }
+
+template <typename T, int CPT>
+__device__ __forceinline__ void storec(T* p, const float (&v)[CPT]) {
+  typename RawC<T, CPT>::type raw;
   if constexpr (sizeof(T) == 2) {
-    uint2 raw;
-    raw.x = pack_bf16x2(v[0], v[1]);
-    raw.y = pack_bf16x2(v[2], v[3]);
-    *reinterpret_cast<uint2*>(p) = raw;
+    if constexpr (CPT == 4) { raw.x = pack_bf16x2(v[0], v[1]); raw.y = pack_bf16x2(v[2], v[3]); }
+    else raw = pack_bf16x2(v[0], v[1]);
   } else {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    if constexpr (CPT == 4) raw = make_float4(v[0], v[1], v[2], v[3]);
+    else raw = make_float2(v[0], v[1]);
   }
+  *reinterpret_cast<typename RawC<T, CPT>::type*>(p) = raw;
 }
 
-template <typename T, bool PRECISE>
+// CPT = 2 for bf16 (about 70 registers, 7 CTAs per SM: the kernel sits on the MUFU pipe and needs the warps),
+// CPT = 4 for the fp32 parity path.
+template <typename T, bool PRECISE, int CPT>
 __global__ void __launch_bounds__(128)
 conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ w_f, const float* __restrict__ b_f,
                  const float* __restrict__ w_r, const float* __restrict__ b_r, T* __restrict__ out_f,
                  T* __restrict__ out_r, int L, int E) {
-  typedef typename Raw4<T>::type raw_t;
-  const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  typedef typename RawC<T, CPT>::type raw_t;
+  const int e0 = (blockIdx.x * blockDim.x + threadIdx.x) * CPT;
   if (e0 >= E) return;
   const int t0 = blockIdx.y * kConvTT;
   const long long seq_row0 = static_cast<long long>(blockIdx.z) * L;
-  float wf[4][4], wr[4][4], bf[4], br[4];
+  float wf[CPT][4], wr[CPT][4], bf[CPT], br[CPT];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < CPT; ++c) {
     const float4 a = *reinterpret_cast<const float4*>(w_f + (e0 + c) * 4);
     const float4 b = *reinterpret_cast<const float4*>(w_r + (e0 + c) * 4);
     wf[c][0] = a.x; wf[c][1] = a.y; wf[c][2] = a.z; wf[c][3] = a.w;
@@ -186,13 +191,13 @@ conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict
   raw_t zero_raw;
   memset(&zero_raw, 0, sizeof(zero_raw));
   auto fetch = [&](int t) -> raw_t {   // row t of this sequence, zero outside [0, L)
-    return (t >= 0 && t < L) ? load4_raw<T>(xcol + (seq_row0 + t) * ldx) : zero_raw;
+    return (t >= 0 && t < L) ? *reinterpret_cast<const raw_t*>(xcol + (seq_row0 + t) * ldx) : zero_raw;
   };
   // win[j] holds x[t - 3 + j], j = 0..6, for the step being computed
-  float win[7][4];
+  float win[7][CPT];
   raw_t nxt[kConvBlk];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) cvt4(fetch(t0 - 3 + j), win[j]);
+  for (int j = 0; j < 6; ++j) cvtc(fetch(t0 - 3 + j), win[j]);
 #pragma unroll
   for (int i = 0; i < kConvBlk; ++i) nxt[i] = fetch(t0 + 3 + i);
 #pragma unroll 1
@@ -208,11 +213,11 @@ conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict
 #pragma unroll
     for (int i = 0; i < kConvBlk; ++i) {
       const int t = t0 + blk + i;
-      cvt4(cur[i], win[6]);
+      cvtc(cur[i], win[6]);
       if (t < L) {
-        float of[4], orv[4];
+        float of[CPT], orv[CPT];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CPT; ++c) {
           float a = bf[c];
           a = fmaf(wf[c][0], win[0][c], a);
           a = fmaf(wf[c][1], win[1][c], a);
@@ -226,13 +231,13 @@ conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict
           r = fmaf(wr[c][3], win[3][c], r);
           orv[c] = silu<PRECISE>(r);
         }
-        store4<T>(out_f + (seq_row0 + t) * E + e0, of);
-        store4<T>(out_r + (seq_row0 + t) * E + e0, orv);
+        storec<T, CPT>(out_f + (seq_row0 + t) * E + e0, of);
+        storec<T, CPT>(out_r + (seq_row0 + t) * E + e0, orv);
       }
 #pragma unroll
       for (int j = 0; j < 6; ++j)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) win[j][c] = win[j + 1][c];
+        for (int c = 0; c < CPT; ++c) win[j][c] = win[j + 1][c];
     }
   }
 }

@@ -280,9 +280,10 @@ int op_conv(pcad_handle* h, const void* x, long long ldx, const float* w_f, cons
             const float* b_r, void* out_f, void* out_r, int S, int L, int E, bool f32, cudaStream_t st) {
   if (E % 4) return fail(h, PCAD_ERR_INVALID, "conv: E must be a multiple of 4");
   if (S <= 0 || L <= 0) return PCAD_OK;
-  dim3 grid((E / 4 + 127) / 128, (L + kConvTT - 1) / kConvTT, S);
-  if (f32) conv_silu_kernel<float, true><<<grid, 128, 0, st>>>(static_cast<const float*>(x), ldx, w_f, b_f, w_r, b_r, static_cast<float*>(out_f), static_cast<float*>(out_r), L, E);
-  else conv_silu_kernel<bf16, false><<<grid, 128, 0, st>>>(static_cast<const bf16*>(x), ldx, w_f, b_f, w_r, b_r, static_cast<bf16*>(out_f), static_cast<bf16*>(out_r), L, E);
+  const int cpt = f32 ? 4 : 2;   // channels per thread
+  dim3 grid((E / cpt + 127) / 128, (L + kConvTT - 1) / kConvTT, S);
+  if (f32) conv_silu_kernel<float, true, 4><<<grid, 128, 0, st>>>(static_cast<const float*>(x), ldx, w_f, b_f, w_r, b_r, static_cast<float*>(out_f), static_cast<float*>(out_r), L, E);
+  else conv_silu_kernel<bf16, false, 2><<<grid, 128, 0, st>>>(static_cast<const bf16*>(x), ldx, w_f, b_f, w_r, b_r, static_cast<bf16*>(out_f), static_cast<bf16*>(out_r), L, E);
   CUDA_TRY(h, cudaGetLastError());
   return PCAD_OK;
 }
