@@ -101,6 +101,18 @@ int pcad_score_masked(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos
 int pcad_score_windows_host(pcad_handle* h, const uint8_t* ascii_host, int B, int L, int token_idx,
                             float* logits4_host, void* stream);
 
+/* Window extraction on the device (seq_from_vcf's slice-and-pad rule, zero_shot_score.py:185-198), for genome-scale
+ * runs where the chromosome is resident in HBM: chrom_dev = chrom_len ASCII bases, pos0_dev = int64 [B] 0-based variant
+ * positions; ascii_out_dev receives uint8 [B, L] upper-cased windows with the variant at index token_idx, padded with
+ * 'N' exactly as the reference pads (right-justified at the chromosome start, left-justified otherwise). */
+int pcad_extract_windows(pcad_handle* h, const uint8_t* chrom_dev, int64_t chrom_len, const int64_t* pos0_dev,
+                         int B, int L, int token_idx, uint8_t* ascii_out_dev, void* stream);
+
+/* pcad_score_windows_host with device buffers: ascii_dev uint8 [B, L] (e.g. from pcad_extract_windows) ->
+ * logits4_dev float32 [B, 4]; tokenise + mask + forward + head on the stream, no copies, no synchronisation. */
+int pcad_score_windows_dev(pcad_handle* h, const uint8_t* ascii_dev, int B, int L, int token_idx,
+                           float* logits4_dev, void* stream);
+
 /* Device tokeniser on its own (bit-exact with the host LUT): ascii_dev [n] -> ids_dev uint8 [n]. */
 int pcad_tokenize(pcad_handle* h, const uint8_t* ascii_dev, int64_t n, uint8_t* ids_dev, void* stream);
 

@@ -18,7 +18,7 @@ STAGES = ("embed", "norm", "in_proj", "conv", "x_proj", "dt_proj", "scan", "out_
 
 EXPORTS = (
     "pcad_abi_version", "pcad_create", "pcad_destroy", "pcad_last_error", "pcad_set_weight", "pcad_finalize",
-    "pcad_set_tokenizer", "pcad_forward", "pcad_score_masked", "pcad_score_windows_host", "pcad_tokenize",
+    "pcad_set_tokenizer", "pcad_forward", "pcad_score_masked", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
     "pcad_workspace_bytes", "pcad_set_profiling", "pcad_get_profile", "pcad_launch_count",
     "pcad_op_linear", "pcad_op_linear_softplus", "pcad_op_linear_residual", "pcad_op_linear_rowscale",
     "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_biscan",
@@ -64,6 +64,8 @@ def load() -> C.CDLL:
     lib.pcad_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     lib.pcad_score_masked.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.pcad_score_windows_host.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.pcad_score_windows_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.pcad_extract_windows.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp, vp]
     lib.pcad_tokenize.argtypes = [vp, vp, i64, vp, vp]
     lib.pcad_workspace_bytes.argtypes = [vp, i32, i32, C.POINTER(C.c_size_t)]
     lib.pcad_set_profiling.argtypes = [vp, i32]

@@ -53,6 +53,36 @@ __global__ void tokenize_kernel(const uint8_t* __restrict__ ascii, uint8_t* __re
   ids[i] = id;
 }
 
+// ---- window extraction on the device (reference seq_from_vcf, src/zero_shot_score.py:185-198) --------------------
+// out[b, k] = the L-base context of the variant at 0-based chromosome position pos0[b], variant at index token_idx:
+// chrom[pos0 - token_idx : pos0 + L - token_idx] upper-cased; windows that would start before the chromosome are
+// right-justified with 'N' (the slice chrom[0 : pos0 + L - token_idx] is kept whole), all others left-justified.
+__global__ void extract_windows_kernel(const uint8_t* __restrict__ chrom, long long chrom_len,
+                                       const long long* __restrict__ pos0, uint8_t* __restrict__ out, int B, int L,
+                                       int token_idx) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * L) return;
+  const int b = static_cast<int>(i / L), k = static_cast<int>(i % L);
+  const long long p = pos0[b];
+  const long long add = L - token_idx;
+  long long src;
+  if (p - token_idx < 0) {
+    long long n_s = p + add;                       // length of chrom[0 : p + add]
+    n_s = n_s < 0 ? 0 : (n_s > chrom_len ? chrom_len : n_s);
+    const long long pad = L - n_s;
+    src = (k < pad) ? -1 : (k - pad);
+  } else {
+    src = p - token_idx + k;
+    if (src >= chrom_len) src = -1;
+  }
+  uint8_t c = 'N';
+  if (src >= 0) {
+    c = chrom[src];
+    if (c >= 'a' && c <= 'z') c -= 32;             // str.upper() on ASCII
+  }
+  out[i] = c;
+}
+
 __global__ void ids64_to_u8_kernel(const long long* __restrict__ in, uint8_t* __restrict__ out, long long n, int V,
                                    int* __restrict__ bad) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -764,6 +764,45 @@ int pcad_tokenize(pcad_handle* h, const uint8_t* ascii_dev, int64_t n, uint8_t* 
   return PCAD_OK;
 }
 
+int pcad_extract_windows(pcad_handle* h, const uint8_t* chrom_dev, int64_t chrom_len, const int64_t* pos0_dev, int B, int L,
+                         int token_idx, uint8_t* ascii_out_dev, void* stream) {
+  if (!h || B < 0 || L <= 0 || chrom_len < 0) return PCAD_ERR_INVALID;
+  if (B == 0) return PCAD_OK;
+  if (!chrom_dev || !pos0_dev || !ascii_out_dev) return fail(h, PCAD_ERR_INVALID, "null argument");
+  if (token_idx < 0 || token_idx >= L) return fail(h, PCAD_ERR_INVALID, "token_idx %d outside [0, %d)", token_idx, L);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  StageTimer tm(h, st, PCAD_ST_MISC);
+  const long long n = static_cast<long long>(B) * L;
+  extract_windows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      chrom_dev, chrom_len, reinterpret_cast<const long long*>(pos0_dev), ascii_out_dev, B, L, token_idx);
+  CUDA_TRY(h, cudaGetLastError());
+  return PCAD_OK;
+}
+
+int pcad_score_windows_dev(pcad_handle* h, const uint8_t* ascii_dev, int B, int L, int token_idx, float* logits4_dev, void* stream) {
+  int rc = check_call(h, B, L);
+  if (rc) return rc;
+  if (B == 0 || L == 0) return PCAD_OK;
+  if (!ascii_dev || !logits4_dev) return fail(h, PCAD_ERR_INVALID, "null argument");
+  if (token_idx < 0 || token_idx >= L) return fail(h, PCAD_ERR_INVALID, "token_idx %d outside [0, %d)", token_idx, L);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B, L);
+  if (rc) return rc;
+  Workspace& ws = h->ws;
+  const long long n = static_cast<long long>(B) * L;
+  {
+    StageTimer tm(h, st, PCAD_ST_MISC, 2);
+    tokenize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ascii_dev, ws.ids, n, h->lut_dev, L, token_idx, h->mask_id);
+    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos, B, token_idx);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  rc = run_backbone(h, B, L, st);
+  if (rc) return rc;
+  return run_head(h, B, L, ws.pos, 1, logits4_dev, st);
+}
+
 int pcad_forward(pcad_handle* h, const int64_t* ids_dev, int B, int L, float* logits_dev, void* hidden_dev, void* stream) {
   int rc = check_call(h, B, L);
   if (rc) return rc;

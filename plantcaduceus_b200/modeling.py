@@ -241,6 +241,34 @@ class CaduceusForMaskedLM:
                                                              C.c_void_p(out.data_ptr()), self._stream()), self._handle)
         return out
 
+    def extract_windows_device(self, chrom_dev: torch.Tensor, pos0: torch.Tensor, token_idx: int = 255,
+                               length: int = 512) -> torch.Tensor:
+        """Windows for variants at 0-based positions ``pos0`` of a chromosome resident on the device: uint8 [B, length],
+        byte-identical to ``genome_io.extract_window`` (the reference's seq_from_vcf slice-and-pad rule)."""
+        self._require_handle()
+        chrom = chrom_dev.to(device=self.device, dtype=torch.uint8).contiguous()
+        pos = pos0.to(device=self.device, dtype=torch.int64).contiguous()
+        B = pos.numel()
+        with torch.cuda.device(self.device):
+            out = torch.empty((B, length), dtype=torch.uint8, device=self.device)
+            if B > 0:
+                _lib.check(self._lib.pcad_extract_windows(self._handle, C.c_void_p(chrom.data_ptr()), chrom.numel(),
+                                                          C.c_void_p(pos.data_ptr()), B, length, int(token_idx),
+                                                          C.c_void_p(out.data_ptr()), self._stream()), self._handle)
+        return out
+
+    def score_windows_device(self, ascii_dev: torch.Tensor, token_idx: int) -> torch.Tensor:
+        """``score_windows_host`` for windows already on the device: uint8 [B, L] -> float32 [B, 4] (device, async)."""
+        self._require_handle()
+        a = ascii_dev.to(device=self.device, dtype=torch.uint8).contiguous()
+        B, L = a.shape
+        with torch.cuda.device(self.device):
+            out = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+            if B > 0:
+                _lib.check(self._lib.pcad_score_windows_dev(self._handle, C.c_void_p(a.data_ptr()), B, L, int(token_idx),
+                                                            C.c_void_p(out.data_ptr()), self._stream()), self._handle)
+        return out
+
     def tokenize_device(self, ascii_dev: torch.Tensor) -> torch.Tensor:
         self._require_handle()
         a = ascii_dev.to(device=self.device, dtype=torch.uint8).contiguous()

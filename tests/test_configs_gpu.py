@@ -116,3 +116,32 @@ def test_zero_shot_eval_helpers_match_reference_formulas(cuda_device):
                     vals.append(0.0)
         want_sv[i] = -float(np.mean(vals))
     assert np.allclose(got_sv, want_sv, rtol=1e-5, atol=1e-7)
+
+
+def test_device_window_extraction_bit_exact_and_genome_scoring(cuda_device):
+    """Config 3 path: windows cut on the device are byte-identical to the host rule (reference seq_from_vcf padding,
+    zero_shot_score.py:185-198), and scoring from positions equals scoring the host-built windows."""
+    from plantcaduceus_b200 import genome_io as gio
+    from plantcaduceus_b200.genome_scan import score_positions
+    from plantcaduceus_b200.modeling import CaduceusForMaskedLM
+    rng = np.random.default_rng(9)
+    chrom = bytes(rng.choice(np.frombuffer(b"ACGTacgtNn", dtype=np.uint8), size=3000))
+    cfg = CaduceusConfig(d_model=128, n_layer=2)
+    model = CaduceusForMaskedLM.from_pretrained(random_init_state_dict(cfg, seed=4), config=cfg,
+                                                torch_dtype=torch.float32).to(cuda_device)
+    chrom_dev = torch.from_numpy(np.frombuffer(chrom, dtype=np.uint8).copy()).to(cuda_device)
+    pos = np.array([0, 1, 254, 255, 256, 300, 1500, 2743, 2744, 2745, 2999] + list(rng.integers(0, 3000, 40)), dtype=np.int64)
+    for tok_idx, length in ((255, 512), (100, 512), (0, 64), (63, 64)):
+        got = model.extract_windows_device(chrom_dev, torch.from_numpy(pos), tok_idx, length).cpu().numpy()
+        for k, p in enumerate(pos):
+            assert bytes(got[k]) == gio.extract_window(chrom, int(p), tok_idx, length), (p, tok_idx, length)
+    # a chromosome shorter than the window: the reference's right-justification quirk is reproduced
+    short = b"ACGTACGTAC"
+    sd = torch.from_numpy(np.frombuffer(short, dtype=np.uint8).copy()).to(cuda_device)
+    got = model.extract_windows_device(sd, torch.tensor([1, 9]), 255, 512).cpu().numpy()
+    assert bytes(got[0]) == gio.extract_window(short, 1, 255) and bytes(got[1]) == gio.extract_window(short, 9, 255)
+    # scoring from positions == scoring host-built windows through the host entry point
+    probs = score_positions(model, chrom, pos, batch_size=16, chrom_dev=chrom_dev)
+    host_windows = np.stack([np.frombuffer(gio.extract_window(chrom, int(p), 255), dtype=np.uint8) for p in pos])
+    want = gio.softmax4(model.score_windows_host(torch.from_numpy(host_windows.copy()).pin_memory(), 255).numpy())
+    assert np.array_equal(probs, want)
