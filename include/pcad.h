@@ -150,12 +150,14 @@ int pcad_op_linear_softplus(const void* A, const void* W, const float* bias, voi
 /* The block's fused residual add + RMSNorm [mamba_ssm rms_norm_fn(prenorm=True)] folded into the two GEMMs around
  * it (bf16 only; what the bf16 forward runs when residual_in_fp32 = 0):
  *   pcad_op_linear_residual:  resid_out = A W^T + resid_in  (fp32 sum, stored bf16; resid_out may alias resid_in),
- *                             sumsq_out[row] += sum_cols (fp32 sum)^2   (caller zeroes sumsq_out; float [M])
- *   pcad_op_linear_rowscale:  C = (A W^T) * rsqrt(sumsq_in[row] / K + eps)   -- RMSNorm of A's rows applied after the
- *                             GEMM; the norm weight must be pre-multiplied into W's columns by the caller. */
+ *                             sumsq_out[row][p] = sum over column tile p of (fp32 sum)^2; float [M, pcad_op_sumsq_parts(N)],
+ *                             every slot is written with a plain store (no atomics: results are deterministic)
+ *   pcad_op_linear_rowscale:  C = (A W^T) * rsqrt(sum_p sumsq_in[row][p] / K + eps)   -- RMSNorm of A's rows applied
+ *                             after the GEMM; the norm weight must be pre-multiplied into W's columns by the caller. */
+int pcad_op_sumsq_parts(int N);
 int pcad_op_linear_residual(const void* A, const void* W, const void* resid_in, void* resid_out, float* sumsq_out,
                             int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ld_res, int dtype, void* stream);
-int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in, float eps, void* C,
+int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in, int sumsq_parts, float eps, void* C,
                             int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream);
 
 /* Fused residual add + RMSNorm [mamba_ssm rms_norm_fn, prenorm=True]:

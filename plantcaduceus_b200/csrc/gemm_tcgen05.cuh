@@ -50,17 +50,20 @@ struct GemmCfg {
 // kEpiResidual / kEpiRowScale fold the block's fused residual-add RMSNorm ([EXT] rms_norm_fn(prenorm=True)) into the
 // two GEMMs around it, so the bf16 forward has no norm kernel between layers:
 //   out_proj, kEpiResidual:  r_new = acc + r_old (fp32), stored as the new residual stream (bf16), and
-//                            sumsq[row] += sum_cols r_new^2 (from the un-rounded fp32 sums, as the reference's stats);
-//   in_proj,  kEpiRowScale:  C = acc * rsqrt(sumsq[row] / K + eps), with the norm weight pre-multiplied into the
-//                            columns of W at load time: (r * rstd * w) W^T == rstd * (r (W diag(w))^T).
+//                            sumsq[row][part] = sum over this tile's columns of r_new^2 (from the un-rounded fp32 sums,
+//                            as the reference's stats); one slot per column tile, plain stores -- no atomics, so the
+//                            forward is deterministic and the two strands stay bit-identical;
+//   in_proj,  kEpiRowScale:  C = acc * rsqrt(sum_parts sumsq[row][.] / K + eps), with the norm weight pre-multiplied
+//                            into the columns of W at load time: (r * rstd * w) W^T == rstd * (r (W diag(w))^T).
 enum { kEpiPlain = 0, kEpiSoftplus = 1, kEpiResidual = 2, kEpiRowScale = 3 };
 
 struct EpiParams {
   const float* bias = nullptr;        // kEpiSoftplus: [N]
   const bf16* resid = nullptr;        // kEpiResidual: [M, N] with row pitch ld_res (may alias C)
   long long ld_res = 0;
-  float* sumsq_out = nullptr;         // kEpiResidual: [M], accumulated with atomicAdd (zeroed by the caller)
-  const float* sumsq_in = nullptr;    // kEpiRowScale: [M]
+  float* sumsq_out = nullptr;         // kEpiResidual: [M, sumsq_parts]; slot = column-tile index (every slot is written)
+  const float* sumsq_in = nullptr;    // kEpiRowScale: [M, sumsq_parts], summed in slot order
+  int sumsq_parts = 1;
   float inv_k = 0.f;                  // kEpiRowScale: 1 / (row length the sum of squares was taken over)
   float eps = 0.f;
 };
@@ -178,7 +181,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const long long grow = static_cast<long long>(m0) + q * 32 + lane;   // this lane's output row
       const bool row_ok = grow < M;
       float row_scale = 0.f, row_ss = 0.f;
-      if constexpr (EPI == kEpiRowScale) row_scale = row_ok ? rsqrtf(ep.sumsq_in[grow] * ep.inv_k + ep.eps) : 0.f;
+      if constexpr (EPI == kEpiRowScale) {
+        float ss = 0.f;
+        if (row_ok)
+          for (int pp = 0; pp < ep.sumsq_parts; ++pp) ss += ep.sumsq_in[grow * ep.sumsq_parts + pp];
+        row_scale = row_ok ? rsqrtf(ss * ep.inv_k + ep.eps) : 0.f;
+      }
 #pragma unroll 1
       for (int c0 = (ew >> 2) * 64; c0 < BN; c0 += kChunkStep) {
         if (n0 + c0 >= N) break;  // warp-uniform
@@ -257,7 +265,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if constexpr (EPI == kEpiResidual) {
-        if (row_ok) atomicAdd(ep.sumsq_out + grow, row_ss);
+        static_assert(EPI != kEpiResidual || EW == 4, "one sum-of-squares slot per column tile assumes one warp per lane quarter");
+        if (row_ok) ep.sumsq_out[grow * ep.sumsq_parts + (n0 / BN)] = row_ss;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -317,6 +326,12 @@ inline int pick_bn(int N) {
   return waste128 < waste256 ? 128 : 256;
 }
 
+// Number of column tiles (= sum-of-squares slots per row) the residual epilogue produces for an N-column output.
+inline int gemm_sumsq_parts(int N) {
+  const int BN = pick_bn(N);
+  return (N + BN - 1) / BN;
+}
+
 template <int BN, int EPI, int EW = 4>
 inline cudaError_t launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, long long M, int N,
                                   int K, const EpiParams& ep, int num_sms, cudaStream_t stream) {
@@ -352,6 +367,10 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
   if (epi == kEpiResidual && (!ep.resid || !ep.sumsq_out || (N % 8) || (ep.ld_res % 8) ||
                               (reinterpret_cast<uintptr_t>(ep.resid) & 15))) {
     *why = "gemm: the residual epilogue needs resid (16-byte aligned, pitch % 8 == 0), sumsq_out and N % 8 == 0";
+    return cudaErrorInvalidValue;
+  }
+  if (epi == kEpiResidual && ep.sumsq_parts != gemm_sumsq_parts(N)) {
+    *why = "gemm: sumsq_parts must equal gemm_sumsq_parts(N)";
     return cudaErrorInvalidValue;
   }
   if (epi == kEpiRowScale && !ep.sumsq_in) {

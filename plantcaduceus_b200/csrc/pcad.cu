@@ -56,7 +56,7 @@ struct Workspace {
   void* dbc[2] = {nullptr, nullptr};    // [T, RP]
   void* delta[2] = {nullptr, nullptr};  // [T, E]
   void* y = nullptr;           // [T, E]
-  float* sumsq[2] = {nullptr, nullptr};  // [T] row sums of squares of the residual stream (fused-norm path)
+  float* sumsq[2] = {nullptr, nullptr};  // [T, parts] per-column-tile sums of squares of the residual stream (fused-norm path)
   uint8_t* ascii = nullptr;    // [B, L] staging for the host entry
   float* logits4 = nullptr;    // [B, 4] staging for the host entry
   int* pos = nullptr;          // [B] staging for the host entry
@@ -146,7 +146,7 @@ __global__ void scale_columns_kernel(const bf16* __restrict__ W, const float* __
   out[i] = __float2bfloat16_rn(__bfloat162float(W[i]) * w[i % cols]);
 }
 // ss[row] = sum_j x[row, j]^2, one warp per row (layer 0 of the fused-norm path: the embedding output)
-__global__ void row_sumsq_kernel(const bf16* __restrict__ x, float* __restrict__ ss, long long rows, int d) {
+__global__ void row_sumsq_kernel(const bf16* __restrict__ x, float* __restrict__ ss, long long rows, int d, int parts) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -158,7 +158,7 @@ __global__ void row_sumsq_kernel(const bf16* __restrict__ x, float* __restrict__
     for (int k = 0; k < 8; ++k) acc = fmaf(v[k], v[k], acc);
   }
   acc = warp_sum(acc);
-  if (lane == 0) ss[row] = acc;
+  if (lane < parts) ss[row * parts + lane] = lane == 0 ? acc : 0.f;   // slot 0 holds the sum, the other slots are zero
 }
 __global__ void neg_exp_kernel(float* __restrict__ a, long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -327,7 +327,8 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
   const size_t o_dbc0 = take(T * h->RP * a), o_dbc1 = take(T * h->RP * a);
   const size_t o_dl0 = take(T * h->E * a), o_dl1 = take(T * h->E * a);
   const size_t o_y = take(T * h->E * a);
-  const size_t o_ss0 = take(T * sizeof(float)), o_ss1 = take(T * sizeof(float));
+  const size_t ss_parts = static_cast<size_t>(gemm_sumsq_parts(h->d));
+  const size_t o_ss0 = take(T * ss_parts * sizeof(float)), o_ss1 = take(T * ss_parts * sizeof(float));
   const size_t o_ascii = take(static_cast<size_t>(B) * L);
   const size_t o_l4 = take(static_cast<size_t>(B) * 4 * sizeof(float));
   const size_t o_pos = take(static_cast<size_t>(B) * sizeof(int));
@@ -372,13 +373,14 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
   // squares in ws.sumsq[cur]; out_proj's epilogue adds into it, in_proj's epilogue applies rstd.  Otherwise the
   // block is norm kernel -> in_proj ... out_proj -> ws.hid, exactly the reference's order of roundings.
   int cur = 0;
+  const int parts = gemm_sumsq_parts(d);
   {
     StageTimer tm(h, st, PCAD_ST_EMBED, fused ? 2 : 1);
     const long long total = T * (d / 8);
     const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
     if (f32) embed_kernel<float><<<blocks, 256, 0, st>>>(ws.ids, static_cast<const float*>(h->emb), static_cast<float*>(ws.hid), B, L, d, h->comp_dev);
     else embed_kernel<bf16><<<blocks, 256, 0, st>>>(ws.ids, static_cast<const bf16*>(h->emb), static_cast<bf16*>(fused ? ws.resid : ws.hid), B, L, d, h->comp_dev);
-    if (fused) row_sumsq_kernel<<<static_cast<unsigned>((T + 7) / 8), 256, 0, st>>>(static_cast<const bf16*>(ws.resid), ws.sumsq[cur], T, d);
+    if (fused) row_sumsq_kernel<<<static_cast<unsigned>((T + 7) / 8), 256, 0, st>>>(static_cast<const bf16*>(ws.resid), ws.sumsq[cur], T, d, parts);
     CUDA_TRY(h, cudaGetLastError());
   }
   for (int li = 0; li < h->cfg.n_layer; ++li) {
@@ -394,6 +396,7 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
       if (fused) {
         EpiParams ep;
         ep.sumsq_in = ws.sumsq[cur];
+        ep.sumsq_parts = parts;
         ep.inv_k = 1.0f / static_cast<float>(d);
         ep.eps = h->cfg.norm_eps;
         rc = op_linear(h, ws.resid, lw.in_proj_s, ws.xz, T, 2 * E, d, d, d, 2 * E, false, h->num_sms, st, kEpiRowScale, ep);
@@ -438,11 +441,11 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
     {
       StageTimer tm(h, st, PCAD_ST_OUT_PROJ);
       if (fused) {
-        CUDA_TRY(h, cudaMemsetAsync(ws.sumsq[cur ^ 1], 0, static_cast<size_t>(T) * sizeof(float), st));
         EpiParams ep;
         ep.resid = static_cast<const bf16*>(ws.resid);
         ep.ld_res = d;
         ep.sumsq_out = ws.sumsq[cur ^ 1];
+        ep.sumsq_parts = parts;
         rc = op_linear(h, ws.y, lw.out_proj, ws.resid, T, d, E, E, E, d, false, h->num_sms, st, kEpiResidual, ep);
         cur ^= 1;
       } else {
@@ -906,6 +909,8 @@ int pcad_get_profile(pcad_handle* h, float ms[PCAD_ST_COUNT], int64_t launches[P
 
 int64_t pcad_launch_count(const pcad_handle* h) { return h ? h->launch_count : 0; }
 
+int pcad_op_sumsq_parts(int N) { return N > 0 ? gemm_sumsq_parts(N) : 0; }
+
 // ---- single-operator entry points ---------------------------------------------------------------------
 static pcad_handle* op_scratch() {
   static pcad_handle scratch;  // only .err and .launch_count are used
@@ -941,14 +946,16 @@ int pcad_op_linear_residual(const void* A, const void* W, const void* resid_in, 
   ep.resid = static_cast<const bf16*>(resid_in);
   ep.ld_res = ld_res;
   ep.sumsq_out = sumsq_out;
+  ep.sumsq_parts = gemm_sumsq_parts(N);
   return op_fail_to_global(op_linear(op_scratch(), A, W, resid_out, M, N, K, lda, ldw, ld_res, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiResidual, ep));
 }
 
-int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in, float eps, void* C, int64_t M, int N, int K,
+int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in, int sumsq_parts, float eps, void* C, int64_t M, int N, int K,
                             int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream) {
-  if (dtype != PCAD_BF16 || !sumsq_in) return PCAD_ERR_INVALID;
+  if (dtype != PCAD_BF16 || !sumsq_in || sumsq_parts < 1) return PCAD_ERR_INVALID;
   EpiParams ep;
   ep.sumsq_in = sumsq_in;
+  ep.sumsq_parts = sumsq_parts;
   ep.inv_k = 1.0f / static_cast<float>(K);
   ep.eps = eps;
   return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiRowScale, ep));

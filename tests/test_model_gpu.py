@@ -104,6 +104,25 @@ def test_l20_fp32_and_bf16_real_shape(Model, cuda_device):
     assert_bf16_parity(got16, want, want16, scored=(slice(None), 255, slice(3, 7)))
 
 
+@pytest.mark.parametrize("name", ["PlantCaduceus_l24", "PlantCaduceus_l28", "PlantCaduceus_l32"])
+def test_published_widths_two_layers(Model, cuda_device, name):
+    """The other published sizes (d 512 / 768 / 1024; x_proj widths 64 / 80 / 96; dt_rank 32 / 48 / 64) at 2 layers so the
+    oracle finishes: every GEMM tile configuration and the real channel counts, fp32 and bf16, residual_in_fp32 on and off."""
+    for res32 in (False, True):
+        cfg = preset(name, n_layer=2, residual_in_fp32=res32)
+        sd = random_init_state_dict(cfg, seed=5)
+        ids = make_ids(2, 512, seed=7, mask_at=255)
+        want, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+        m32 = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.float32).to(cuda_device)
+        assert rel_err(m32(input_ids=ids.to(cuda_device)).logits.cpu(), want) <= 1e-4
+        del m32
+        m16 = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+        got16 = m16(input_ids=ids.to(cuda_device)).logits.cpu()
+        want16, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.bfloat16)
+        assert_bf16_parity(got16, want, want16, scored=(slice(None), 255, slice(3, 7)))
+        del m16
+
+
 def test_bf16_fused_norm_matches_unfused(Model, cuda_device, monkeypatch):
     """The bf16 forward folds add+RMSNorm into the out_proj / in_proj epilogues; PCAD_NO_FUSED_NORM=1 runs the
     separate norm kernel instead.  Both must sit at the same distance from the fp32 oracle."""
@@ -204,3 +223,32 @@ def test_errors_are_reported_not_fatal(Model, cuda_device):
     m.to(cuda_device)
     out = m(input_ids=torch.zeros(0, 8, dtype=torch.long, device=cuda_device))
     assert out.logits.shape == (0, 8, 8)
+
+
+def test_full_size_l32_properties(Model, cuda_device):
+    """BASELINE.json configs[1] at full model size (PlantCaduceus_l32, 32 layers, bf16, 512-bp windows), where the CPU
+    oracle is too slow to be the checker: size-independent properties instead.
+      * RC equivariance: the hidden states of RC(ids) are the flipped hidden states of ids, bit for bit (both strands run
+        the same kernels on the same numbers), and the logits agree to fp32 summation order;
+      * batch independence: a window scores the same alone, inside a batch, and through every entry point;
+      * determinism: two runs are bit-identical."""
+    cfg = preset("PlantCaduceus_l32")
+    sd = random_init_state_dict(cfg, seed=0)
+    model = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    B, L, idx = 24, 512, 255
+    ids = make_ids(B, L, seed=31, mask_at=idx)
+    comp = torch.tensor([cfg.complement_map[i] for i in range(8)])
+    a = model(input_ids=ids.to(cuda_device), output_hidden_states=True)
+    b = model(input_ids=O.reverse_complement_ids(ids, cfg).to(cuda_device), output_hidden_states=True)
+    assert torch.equal(b.hidden_states[-1].cpu(), a.hidden_states[-1].cpu().flip(1, 2))
+    assert (b.logits.cpu() - a.logits.cpu().flip(1)[..., comp]).abs().max().item() <= 1e-4
+    assert torch.isfinite(a.logits).all()
+    # batch independence + entry points
+    acgt = [3, 4, 5, 6]
+    full = a.logits[:, idx, acgt].cpu()
+    alone = model(input_ids=ids[5:6].to(cuda_device)).logits[:, idx, acgt].cpu()
+    assert torch.equal(alone[0], full[5])
+    masked = model.score_masked(ids.to(torch.uint8), torch.full((B, 1), idx, dtype=torch.int32)).cpu()[:, 0]
+    assert torch.equal(masked, full)
+    again = model(input_ids=ids.to(cuda_device)).logits.cpu()
+    assert torch.equal(again, a.logits.cpu())

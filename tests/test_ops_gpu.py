@@ -75,13 +75,14 @@ def test_linear_residual_and_rowscale_epilogues(lib, cuda_device, M, N, K):
     W = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda_device, torch.bfloat16)
     resid = torch.randn(M, N, generator=g).to(cuda_device, torch.bfloat16)
     resid_io = resid.clone()
-    sumsq = torch.zeros(M, device=cuda_device)
+    parts = lib.pcad_op_sumsq_parts(N)
+    sumsq = torch.full((M, parts), float("nan"), device=cuda_device)
     check(lib, lib.pcad_op_linear_residual(ptr(A), ptr(W), ptr(resid_io), ptr(resid_io), ptr(sumsq), M, N, K, K, K, N, BF16, stream()))
     torch.cuda.synchronize()
     want = A.float() @ W.float().t() + resid.float()
     assert (resid_io.float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() + 1e-3
     want_ss = want.pow(2).sum(-1)
-    assert torch.allclose(sumsq, want_ss, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(sumsq.sum(-1), want_ss, rtol=1e-4, atol=1e-3)
     # row scale: C = (X Wn^T) * rsqrt(mean(X^2) + eps), sums of squares taken from above
     d = N
     X = resid_io                                   # [M, d] plays the residual stream
@@ -90,7 +91,7 @@ def test_linear_residual_and_rowscale_epilogues(lib, cuda_device, M, N, K):
     W2s = (W2.float() * w_norm[None, :]).to(torch.bfloat16)
     out = torch.full((M, 2 * d), float("nan"), device=cuda_device, dtype=torch.bfloat16)
     eps = 1e-5
-    check(lib, lib.pcad_op_linear_rowscale(ptr(X), ptr(W2s), ptr(sumsq), C.c_float(eps), ptr(out), M, 2 * d, d, d, d, 2 * d, BF16, stream()))
+    check(lib, lib.pcad_op_linear_rowscale(ptr(X), ptr(W2s), ptr(sumsq), parts, C.c_float(eps), ptr(out), M, 2 * d, d, d, d, 2 * d, BF16, stream()))
     torch.cuda.synchronize()
     normed = (want * torch.rsqrt(want.pow(2).mean(-1, keepdim=True) + eps) * w_norm[None, :])
     ref = normed @ W2.float().t()
