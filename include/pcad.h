@@ -175,6 +175,14 @@ int pcad_op_conv_silu(const void* x, int64_t ldx, const float* w_f, const float*
                       const float* w_r, const float* b_r, void* out_f, void* out_r,
                       int S, int L, int E, int dtype, void* stream);
 
+/* pcad_op_conv_silu and both directions' x_proj in one kernel (bf16 only; needs L % 128 == 0, E % 64 == 0 and
+ * RP in {64, 80, 96}): out_f / out_r as pcad_op_conv_silu; dbc_f = out_f wx_f^T, dbc_r = out_r wx_r^T with wx_*: [RP, E]
+ * bf16 (rows beyond dt_rank + 32 zero) and dbc_*: [S*L, RP].  The conv output goes to global memory for the scan and,
+ * from the same registers, into the shared-memory A operand of the tcgen05 GEMM, so x_proj re-reads nothing. */
+int pcad_op_conv_xproj(const void* x, int64_t ldx, const float* w_f, const float* b_f, const float* w_r, const float* b_r,
+                       void* out_f, void* out_r, const void* wx_f, const void* wx_r, void* dbc_f, void* dbc_r,
+                       int S, int L, int E, int RP, int dtype, void* stream);
+
 /* Bidirectional selective scan with softplus(delta + bias), D skip and SiLU(z) gate
  * [selective_scan_fn(..., delta_softplus=True)], both directions summed before the gate
  * [BiMambaWrapper, strategy "add"]:

@@ -15,6 +15,7 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tcgen05.cuh"
+#include "conv_xproj.cuh"
 #include "scan.cuh"
 
 using namespace pcad;
@@ -71,6 +72,7 @@ struct pcad_handle {
   int d = 0, E = 0, N = 16, R = 0, RP = 0, V = 8;
   bool f32 = false;
   bool dt_softplus_epilogue = false;   // bf16: softplus(dt_proj + bias) in the GEMM epilogue, scan takes delta as is
+  bool fuse_conv_xproj = false;   // bf16: conv + SiLU + both x_proj GEMMs in one kernel (L % 128 == 0)
   bool fuse_norm = false;   // bf16 activations + bf16 residual: add+RMSNorm folded into the out_proj / in_proj epilogues
   size_t act_size = 2;
   bool finalized = false;
@@ -288,6 +290,19 @@ int op_conv(pcad_handle* h, const void* x, long long ldx, const float* w_f, cons
   return PCAD_OK;
 }
 
+int op_conv_xproj(pcad_handle* h, const void* x, long long ldx, const float* w_f, const float* b_f, const float* w_r,
+                  const float* b_r, void* xc_f, void* xc_r, const void* wx_f, const void* wx_r, void* dbc_f, void* dbc_r,
+                  int S, int L, int E, int RP, int num_sms, cudaStream_t st) {
+  if (S <= 0 || L <= 0) return PCAD_OK;
+  const char* why = nullptr;
+  cudaError_t e = conv_xproj_bf16(static_cast<const bf16*>(x), ldx, w_f, b_f, w_r, b_r, static_cast<bf16*>(xc_f),
+                                  static_cast<bf16*>(xc_r), static_cast<const bf16*>(wx_f), static_cast<const bf16*>(wx_r),
+                                  static_cast<bf16*>(dbc_f), static_cast<bf16*>(dbc_r), static_cast<long long>(S) * L, L, E, RP,
+                                  num_sms, st, &why);
+  if (e != cudaSuccess) return fail(h, why ? PCAD_ERR_INVALID : PCAD_ERR_CUDA, "%s", why ? why : cudaGetErrorString(e));
+  return PCAD_OK;
+}
+
 int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* bc_f, const void* u_r,
               const void* delta_r, const void* bc_r, long long ldbc, int bc_off, const void* z, long long ldz,
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
@@ -405,13 +420,20 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
       }
       if (rc) return rc;
     }
-    {
+    const bool fuse_cx = h->fuse_conv_xproj && conv_xproj_supported(L, E, RP);
+    if (fuse_cx) {
+      // conv + SiLU for both directions and both x_proj GEMMs in one kernel (conv_xproj.cuh); timed under "conv"
+      StageTimer tm(h, st, PCAD_ST_CONV);
+      rc = op_conv_xproj(h, ws.xz, 2 * E, lw.dir[0].conv_w, lw.dir[0].conv_b, lw.dir[1].conv_w, lw.dir[1].conv_b, ws.xc[0], ws.xc[1],
+                         lw.dir[0].x_proj, lw.dir[1].x_proj, ws.dbc[0], ws.dbc[1], S, L, E, RP, h->num_sms, st);
+      if (rc) return rc;
+    } else {
       StageTimer tm(h, st, PCAD_ST_CONV);
       rc = op_conv(h, ws.xz, 2 * E, lw.dir[0].conv_w, lw.dir[0].conv_b, lw.dir[1].conv_w, lw.dir[1].conv_b, ws.xc[0], ws.xc[1], S, L, E, f32, st);
       if (rc) return rc;
     }
     for (int dir = 0; dir < 2; ++dir) {
-      {
+      if (!fuse_cx) {
         StageTimer tm(h, st, PCAD_ST_X_PROJ);
         rc = op_linear(h, ws.xc[dir], lw.dir[dir].x_proj, ws.dbc[dir], T, RP, E, E, E, RP, f32, h->num_sms, st);
         if (rc) return rc;
@@ -539,6 +561,8 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   h->f32 = cfg->dtype == PCAD_F32;
   h->act_size = h->f32 ? 4 : 2;
   h->fuse_norm = !h->f32 && !cfg->residual_in_fp32;
+  h->fuse_conv_xproj = false;   // measured slower than conv + 2 x_proj GEMMs (see conv_xproj.cuh); opt-in for experiments
+  if (const char* fc = getenv("PCAD_FUSED_CONV_XPROJ")) h->fuse_conv_xproj = !h->f32 && fc[0] == '1';
   // Off by default: measured zero-sum on B200 (l32, B = 256: scan -11.5 ms, dt_proj +12.3 ms per step), so the
   // forward keeps the reference's order of operations; PCAD_DT_SOFTPLUS_EPILOGUE=1 switches it on for experiments.
   h->dt_softplus_epilogue = false;
@@ -970,6 +994,14 @@ int pcad_op_add_rmsnorm(const void* x, const void* res_in, const float* w, void*
 int pcad_op_conv_silu(const void* x, int64_t ldx, const float* w_f, const float* b_f, const float* w_r, const float* b_r, void* out_f, void* out_r, int S, int L, int E, int dtype, void* stream) {
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_conv(op_scratch(), x, ldx, w_f, b_f, w_r, b_r, out_f, out_r, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream)));
+}
+
+int pcad_op_conv_xproj(const void* x, int64_t ldx, const float* w_f, const float* b_f, const float* w_r, const float* b_r,
+                       void* out_f, void* out_r, const void* wx_f, const void* wx_r, void* dbc_f, void* dbc_r,
+                       int S, int L, int E, int RP, int dtype, void* stream) {
+  if (dtype != PCAD_BF16) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_conv_xproj(op_scratch(), x, ldx, w_f, b_f, w_r, b_r, out_f, out_r, wx_f, wx_r, dbc_f, dbc_r, S, L, E, RP,
+                                         op_num_sms(), static_cast<cudaStream_t>(stream)));
 }
 
 int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f, const void* u_r, const void* delta_r, const void* bc_r,

@@ -179,6 +179,41 @@ def test_conv_silu_both_directions(lib, cuda_device, dtype, S, L, E):
     assert torch.allclose(orv.cpu().float(), want_r, **tol)
 
 
+@pytest.mark.parametrize("S,L,E,R", [(2, 128, 256, 24), (3, 256, 768, 24), (2, 512, 1536, 48), (1, 128, 2048, 64), (5, 384, 1024, 32)])
+def test_conv_xproj_fused(lib, cuda_device, S, L, E, R):
+    """Fused conv + SiLU + both x_proj GEMMs == pcad_op_conv_silu followed by pcad_op_linear (same roundings: the GEMM
+    consumes the bf16-rounded conv output in both cases)."""
+    g = torch.Generator().manual_seed(S * 31 + L + E)
+    RP = (R + 32 + 15) // 16 * 16
+    xz = torch.randn(S * L, 2 * E, generator=g).to(cuda_device, torch.bfloat16)
+    w = [(torch.randn(E, 4, generator=g) * 0.5).to(cuda_device) for _ in range(2)]
+    b = [(torch.randn(E, generator=g) * 0.5).to(cuda_device) for _ in range(2)]
+    wx = []
+    for _ in range(2):
+        m = torch.zeros(RP, E)
+        m[:R + 32] = torch.randn(R + 32, E, generator=g) / E ** 0.5
+        wx.append(m.to(cuda_device, torch.bfloat16))
+    bf = dict(device=cuda_device, dtype=torch.bfloat16)
+    of, orv = torch.full((S * L, E), float("nan"), **bf), torch.full((S * L, E), float("nan"), **bf)
+    df, dr = torch.full((S * L, RP), float("nan"), **bf), torch.full((S * L, RP), float("nan"), **bf)
+    check(lib, lib.pcad_op_conv_xproj(ptr(xz), 2 * E, ptr(w[0]), ptr(b[0]), ptr(w[1]), ptr(b[1]), ptr(of), ptr(orv),
+                                      ptr(wx[0]), ptr(wx[1]), ptr(df), ptr(dr), S, L, E, RP, BF16, stream()))
+    of2, or2 = torch.empty_like(of), torch.empty_like(orv)
+    check(lib, lib.pcad_op_conv_silu(ptr(xz), 2 * E, ptr(w[0]), ptr(b[0]), ptr(w[1]), ptr(b[1]), ptr(of2), ptr(or2), S, L, E, BF16, stream()))
+    d2 = [torch.empty_like(df), torch.empty_like(dr)]
+    for k, src in enumerate((of2, or2)):
+        check(lib, lib.pcad_op_linear(ptr(src), ptr(wx[k]), ptr(d2[k]), S * L, RP, E, E, E, RP, BF16, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(of, of2) and torch.equal(orv, or2)          # same conv arithmetic, bit for bit
+    for got, want in ((df, d2[0]), (dr, d2[1])):
+        assert not torch.isnan(got.float()).any()
+        # both accumulate the same bf16 products in fp32; only the summation order inside the tensor core may differ
+        assert (got.float() - want.float()).abs().max().item() <= 2 ** -7 * want.float().abs().max().item() + 1e-3
+    # unsupported shapes are refused, not mis-computed
+    assert lib.pcad_op_conv_xproj(ptr(xz), 2 * E, ptr(w[0]), ptr(b[0]), ptr(w[1]), ptr(b[1]), ptr(of), ptr(orv),
+                                  ptr(wx[0]), ptr(wx[1]), ptr(df), ptr(dr), S, L - 1, E, RP, BF16, stream()) != 0
+
+
 @pytest.mark.parametrize("dtype,delta_final", [(F32, 0), (BF16, 0), (BF16, 1), (F32, 1)])
 @pytest.mark.parametrize("S,L,E,R", [(2, 512, 256, 24), (3, 64, 128, 8), (2, 37, 128, 8), (1, 1, 128, 8), (2, 16, 128, 64), (1, 33, 384, 24),
                                      (1, 40, 128, 8), (1, 47, 200, 8)])

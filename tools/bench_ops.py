@@ -89,6 +89,21 @@ def main():
         out["conv_ms"] = ms
         out["conv_GBs"] = T * E * 2 * 3 / ms / 1e6
         del xz, of, orv
+    if "conv_xproj" in ops:
+        xz = rnd(T, 2 * E)
+        w = torch.randn(E, 4, device=dev, generator=g)
+        b = torch.randn(E, device=dev, generator=g)
+        wx = rnd(RP, E, scale=E ** -0.5)
+        of, orv = torch.empty(T, E, **bf), torch.empty(T, E, **bf)
+        df, dr = torch.empty(T, RP, **bf), torch.empty(T, RP, **bf)
+        def f():
+            rc = lib.pcad_op_conv_xproj(ptr(xz), 2 * E, ptr(w), ptr(b), ptr(w), ptr(b), ptr(of), ptr(orv), ptr(wx), ptr(wx),
+                                        ptr(df), ptr(dr), S, L, E, RP, BF16, st)
+            assert rc == 0, lib.pcad_last_error(None)
+        ms = timeit(f)
+        out["conv_xproj_ms"] = ms
+        out["conv_xproj_GBs"] = T * E * 2 * 3 / ms / 1e6
+        del xz, of, orv, df, dr
     if "norm" in ops:
         x, r = rnd(T, d), rnd(T, d)
         w = torch.ones(d, device=dev)
