@@ -14,6 +14,20 @@ namespace pcad {
 
 typedef __nv_bfloat16 bf16;
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember which devices have it for one kernel.
+// `done` is a function-local static of the (templated) launcher, one per kernel instantiation.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long long& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done |= bit;
+  return e;
+}
+
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

@@ -272,12 +272,9 @@ inline cudaError_t launch_conv_xproj_rp(const bf16* x, long long ldx, const floa
                                         const CUtensorMap& twr, bf16* dbc_f, bf16* dbc_r, long long T, int L, int E,
                                         int num_sms, cudaStream_t stream) {
   using Cfg = CxCfg<RP>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_xproj_kernel<RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  cudaError_t e = ensure_dynamic_smem(conv_xproj_kernel<RP>, Cfg::kSmemBytes, attr_done);
+  if (e != cudaSuccess) return e;
   const long long tiles = T / kCxTile;
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
   conv_xproj_kernel<RP><<<grid, kCxThreads, Cfg::kSmemBytes, stream>>>(x, ldx, w_f, b_f, w_r, b_r, xc_f, xc_r, twf, twr, dbc_f,

@@ -336,13 +336,9 @@ template <int BN, int EPI, int EW = 4>
 inline cudaError_t launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, long long M, int N,
                                   int K, const EpiParams& ep, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, EW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  cudaError_t e = ensure_dynamic_smem(gemm_bf16_tcgen05_kernel<BN, EPI, EW>, Cfg::kSmemBytes, attr_done);
+  if (e != cudaSuccess) return e;
   const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
   const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
   gemm_bf16_tcgen05_kernel<BN, EPI, EW><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, ep);

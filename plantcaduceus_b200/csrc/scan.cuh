@@ -305,13 +305,9 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
                                  cudaStream_t stream) {
   size_t smem = sizeof(ScanShared<T>);
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e1 = cudaFuncSetAttribute(biscan_kernel<T, PRECISE, DFINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(smem));
-    if (e1 != cudaSuccess) return e1;
-    attr_set = true;
-  }
+  static unsigned long long attr_done = 0;
+  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, DFINAL>, static_cast<int>(smem), attr_done);
+  if (e1 != cudaSuccess) return e1;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
   biscan_kernel<T, PRECISE, DFINAL><<<grid, kScanThreads, smem, stream>>>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z,
                                                                 ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E);

@@ -252,3 +252,17 @@ def test_full_size_l32_properties(Model, cuda_device):
     assert torch.equal(masked, full)
     again = model(input_ids=ids.to(cuda_device)).logits.cpu()
     assert torch.equal(again, a.logits.cpu())
+
+
+def test_two_devices_in_one_process(Model, cuda_device):
+    """Distinct handles are independent (include/pcad.h): two engines on two GPUs of one process give the same bits."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = CaduceusConfig(d_model=256, n_layer=3)
+    sd = random_init_state_dict(cfg, seed=13)
+    ids = make_ids(4, 256, seed=3, mask_at=128)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(dev)
+        outs.append(m(input_ids=ids.to(dev)).logits.cpu())
+    assert torch.equal(outs[0], outs[1])
