@@ -34,7 +34,7 @@ def main():
     L, B = 8192, args.long_batch
     ids = torch.randint(3, 7, (B, L), device=dev)
     for _ in range(2):
-        model(input_ids=ids, output_hidden_states=True, compute_logits=False) if False else model.forward(ids, output_hidden_states=True, compute_logits=False)
+        model.forward(ids, output_hidden_states=True, compute_logits=False)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
