@@ -23,16 +23,19 @@ constexpr int kGemmBK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 // chunks) for epilogues that do real math per element (softplus) -- with one warp per scheduler that math is
 // latency-bound.  The EW = 8 configuration keeps only 2 ring stages (it is used with K <= 64, one k-block per tile)
 // so that the 8 x 2 staging slabs fit.
-template <int BN, int EW>
+// CG = CTAs per tile: 1, or 2 = a CTA pair (cluster of two on one TPC) computing a 256 x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, so a stage is 32 KB
+// instead of 48 KB (6 stages instead of 4) and B crosses shared memory once per 256 output rows.
+template <int BN, int EW, int CG = 1>
 struct GemmCfg {
   static constexpr int kThreads = 64 + 32 * EW;
   static constexpr int kABytes = kGemmBM * kGemmBK * 2;
-  static constexpr int kBBytes = BN * kGemmBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kGemmBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // B tiles must keep 1024-byte alignment inside the ring: pad each B slot to a multiple of 1024.
   static constexpr int kBSlot = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kSlot = kABytes + kBSlot;
-  static constexpr int kStages = (EW == 8) ? 2 : ((BN >= 256) ? 4 : 6);
+  static constexpr int kStages = (EW == 8) ? 2 : ((BN >= 256 && CG == 1) ? 4 : 6);
   static constexpr int kAccStride = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kBarBytes = 256;
@@ -68,11 +71,11 @@ struct EpiParams {
   float eps = 0.f;
 };
 
-template <int BN, int EPI, int EW>
-__global__ void __launch_bounds__(GemmCfg<BN, EW>::kThreads, 1)
+template <int BN, int EPI, int EW, int CG>
+__global__ void __launch_bounds__(GemmCfg<BN, EW, CG>::kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_c, long long M, int N, int K, const EpiParams ep) {
-  using Cfg = GemmCfg<BN, EW>;
+  using Cfg = GemmCfg<BN, EW, CG>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -87,9 +90,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_n = (N + BN - 1) / BN;
-  const long long tiles_m = (M + kGemmBM - 1) / kGemmBM;
+  const long long tiles_m = (M + kGemmBM * CG - 1) / (kGemmBM * CG);   // a tile is (128 * CG) x BN, one per CTA group
   const long long num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + kGemmBK - 1) / kGemmBK;
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs)
+  const long long group_id = blockIdx.x / CG, num_groups = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -101,16 +106,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 32 * EW);
+      mbar_init(&tmem_empty[a], 32 * EW * CG);   // the leader's barrier collects both CTAs' epilogue warps
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2<Cfg::kTmemCols>(tmem_ptr);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // barrier inits of both CTAs visible before any remote arrive / TMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -118,28 +129,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = static_cast<int>(tile / tiles_n) * kGemmBM;
-        const int n0 = static_cast<int>(tile % tiles_n) * BN;
+      for (long long tile = group_id; tile < num_tiles; tile += num_groups) {
+        const int m0 = static_cast<int>(tile / tiles_n) * (kGemmBM * CG) + cta_rank * kGemmBM;   // this CTA's 128 rows
+        const int n0 = static_cast<int>(tile % tiles_n) * BN + cta_rank * (BN / CG);             // this CTA's share of B
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = ring + stage * Cfg::kSlot;
           uint8_t* b_dst = a_dst + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(a_dst, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
-          tma_load_2d(b_dst, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+          if constexpr (CG == 2) {
+            // both CTAs' bytes are credited to the leader's barrier, which alone is armed (with the pair's total)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_cg2(a_dst, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+            tma_load_2d_cg2(b_dst, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(a_dst, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+            tma_load_2d(b_dst, &tmap_b, &full_bar[stage], kb * kGemmBK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN);
+    if (cta_rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM * CG, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (long long tile = group_id; tile < num_tiles; tile += num_groups) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
@@ -153,12 +171,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2) umma_bf16_ss_cg2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above have read it
+          // frees this smem slot (in both CTAs of a pair) once the MMAs above have read it
+          if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        // accumulator complete (each CTA's epilogue waits on its own barrier)
+        if constexpr (CG == 2) umma_commit_cg2(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -172,8 +193,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = static_cast<int>(tile / tiles_n) * kGemmBM;
+    for (long long tile = group_id; tile < num_tiles; tile += num_groups) {
+      const int m0 = static_cast<int>(tile / tiles_n) * (kGemmBM * CG) + cta_rank * kGemmBM;
       const int n0 = static_cast<int>(tile % tiles_n) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -263,7 +284,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         buf ^= 1;
       }
       tc_fence_before();
-      mbar_arrive(&tmem_empty[acc]);
+      if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]);
       if constexpr (EPI == kEpiResidual) {
         static_assert(EPI != kEpiResidual || EW == 4, "one sum-of-squares slot per column tile assumes one warp per lane quarter");
         if (row_ok) ep.sumsq_out[grow * ep.sumsq_parts + (n0 / BN)] = row_ss;
@@ -274,10 +295,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer may still be arriving on / reading this CTA's shared memory
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -332,23 +355,42 @@ inline int gemm_sumsq_parts(int N) {
   return (N + BN - 1) / BN;
 }
 
-template <int BN, int EPI, int EW = 4>
+template <int BN, int EPI, int EW = 4, int CG = 1>
 inline cudaError_t launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, long long M, int N,
                                   int K, const EpiParams& ep, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, EW>;
+  using Cfg = GemmCfg<BN, EW, CG>;
   static unsigned long long attr_done = 0;
-  cudaError_t e = ensure_dynamic_smem(gemm_bf16_tcgen05_kernel<BN, EPI, EW>, Cfg::kSmemBytes, attr_done);
+  cudaError_t e = ensure_dynamic_smem(gemm_bf16_tcgen05_kernel<BN, EPI, EW, CG>, Cfg::kSmemBytes, attr_done);
   if (e != cudaSuccess) return e;
-  const long long tiles = ((M + kGemmBM - 1) / kGemmBM) * ((N + BN - 1) / BN);
-  const int grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
-  gemm_bf16_tcgen05_kernel<BN, EPI, EW><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, ep);
-  return cudaGetLastError();
+  const long long tiles = ((M + kGemmBM * CG - 1) / (kGemmBM * CG)) * ((N + BN - 1) / BN);
+  const long long groups = num_sms / CG;
+  const int grid = static_cast<int>(tiles < groups ? tiles : groups) * CG;
+  if constexpr (CG == 1) {
+    gemm_bf16_tcgen05_kernel<BN, EPI, EW, 1><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, M, N, K, ep);
+    return cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, EPI, EW, CG>, ta, tb, tc, M, N, K, ep);
+  }
 }
 
 // Returns cudaSuccess or an error; *why is set for non-CUDA failures.  `epi` selects the epilogue (EpiParams).
+// cta_pair: use the 2-CTA (cta_group::2) kernel when the shape allows it (N a multiple of 256, K >= 256).
 inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long long M, int N, int K, long long lda,
                                      long long ldw, long long ldc, int num_sms, cudaStream_t stream,
-                                     const char** why, int epi = kEpiPlain, const EpiParams& ep = EpiParams()) {
+                                     const char** why, int epi = kEpiPlain, const EpiParams& ep = EpiParams(),
+                                     bool cta_pair = false) {
   *why = nullptr;
   if (M <= 0 || N <= 0 || K <= 0) return cudaSuccess;
   if ((lda % 8) || (ldw % 8) || (ldc % 8) || (reinterpret_cast<uintptr_t>(A) & 15) ||
@@ -374,11 +416,19 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
     return cudaErrorInvalidValue;
   }
   const int BN = pick_bn(N);
+  const bool pair = cta_pair && BN == 256 && (N % 256) == 0 && K >= 256 && epi != kEpiSoftplus && num_sms >= 2;
   CUtensorMap ta, tb, tc;
-  if (!make_tmap_bf16(&ta, A, M, K, lda, kGemmBM) || !make_tmap_bf16(&tb, W, N, K, ldw, BN) ||
+  if (!make_tmap_bf16(&ta, A, M, K, lda, kGemmBM) || !make_tmap_bf16(&tb, W, N, K, ldw, pair ? BN / 2 : BN) ||
       !make_tmap_bf16(&tc, C, M, N, ldc, 32)) {
     *why = "gemm: cuTensorMapEncodeTiled failed";
     return cudaErrorInvalidValue;
+  }
+  if (pair) {
+    switch (epi) {
+      case kEpiResidual: return launch_gemm_bn<256, kEpiResidual, 4, 2>(ta, tb, tc, M, N, K, ep, num_sms, stream);
+      case kEpiRowScale: return launch_gemm_bn<256, kEpiRowScale, 4, 2>(ta, tb, tc, M, N, K, ep, num_sms, stream);
+      default: return launch_gemm_bn<256, kEpiPlain, 4, 2>(ta, tb, tc, M, N, K, ep, num_sms, stream);
+    }
   }
 #define PCAD_GEMM_EPI(BNV)                                                                                  \
   switch (epi) {                                                                                            \

@@ -235,6 +235,16 @@ struct StageTimer {
 };
 
 // ---- operator launchers (shared by the forward pass and the pcad_op_* entry points) -------------
+// The CTA-pair (tcgen05 cta_group::2) GEMM is used for the wide GEMMs unless PCAD_GEMM_2CTA=0.
+bool gemm_cta_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PCAD_GEMM_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int op_linear(pcad_handle* h, const void* A, const void* W, void* C, long long M, int N, int K, long long lda,
               long long ldw, long long ldc, bool f32, int num_sms, cudaStream_t st, int epi = kEpiPlain,
               const EpiParams& ep = EpiParams()) {
@@ -243,7 +253,7 @@ int op_linear(pcad_handle* h, const void* A, const void* W, void* C, long long M
     CUDA_TRY(h, gemm_f32_simt(static_cast<const float*>(A), static_cast<const float*>(W), static_cast<float*>(C), M, N, K, lda, ldw, ldc, st));
   } else {
     const char* why = nullptr;
-    cudaError_t e = gemm_bf16_tcgen05(static_cast<const bf16*>(A), static_cast<const bf16*>(W), static_cast<bf16*>(C), M, N, K, lda, ldw, ldc, num_sms, st, &why, epi, ep);
+    cudaError_t e = gemm_bf16_tcgen05(static_cast<const bf16*>(A), static_cast<const bf16*>(W), static_cast<bf16*>(C), M, N, K, lda, ldw, ldc, num_sms, st, &why, epi, ep, gemm_cta_pair_enabled());
     if (e != cudaSuccess) return fail(h, why ? PCAD_ERR_INVALID : PCAD_ERR_CUDA, "%s", why ? why : cudaGetErrorString(e));
   }
   return PCAD_OK;

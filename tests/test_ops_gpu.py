@@ -34,6 +34,8 @@ def check(lib, rc):
     (128, 256, 64), (256, 256, 128), (1024, 1536, 384), (2048, 4096, 1024), (1024, 1024, 2048),
     (1000, 96, 2048), (1024, 64, 768), (520, 80, 1536), (1024, 2048, 64), (1024, 768, 24), (77, 384, 768),
     (128, 8, 64), (4096, 3072, 768),
+    # CTA-pair (cta_group::2) kernel: N % 256 == 0 and K >= 256, with M tails on either CTA of the last pair
+    (256, 256, 256), (257, 512, 256), (383, 256, 320), (129, 1024, 1024), (5000, 2048, 512),
 ])
 def test_linear_bf16_tcgen05(lib, cuda_device, M, N, K):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
