@@ -246,20 +246,42 @@ conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict
       cvtc(cur[i], win[6]);
       if (t < L) {
         float of[CPT], orv[CPT];
+        if constexpr (!PRECISE && CPT == 2) {
+          // bf16 fast path: the two channels of a thread ride in one fp32x2 register pair (FFMA2 / FMUL2 / FADD2: half
+          // the issue slots), so the kernel is left with its MUFU work (ex2 + rcp per output) and its HBM traffic
+          f32x2 a2 = pack2(bf[0], bf[1]), r2 = pack2(br[0], br[1]);
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          float a = bf[c];
-          a = fmaf(wf[c][0], win[0][c], a);
-          a = fmaf(wf[c][1], win[1][c], a);
-          a = fmaf(wf[c][2], win[2][c], a);
-          a = fmaf(wf[c][3], win[3][c], a);
-          of[c] = silu<PRECISE>(a);
-          float r = br[c];
-          r = fmaf(wr[c][0], win[6][c], r);
-          r = fmaf(wr[c][1], win[5][c], r);
-          r = fmaf(wr[c][2], win[4][c], r);
-          r = fmaf(wr[c][3], win[3][c], r);
-          orv[c] = silu<PRECISE>(r);
+          for (int k = 0; k < 4; ++k) {
+            a2 = fma2(pack2(wf[0][k], wf[1][k]), pack2(win[k][0], win[k][1]), a2);
+            r2 = fma2(pack2(wr[0][k], wr[1][k]), pack2(win[6 - k][0], win[6 - k][1]), r2);
+          }
+          const f32x2 nl2 = pack2(-kLog2e, -kLog2e), one2 = pack2(1.0f, 1.0f);
+          float xa0, xa1, xr0, xr1;
+          unpack2(mul2(a2, nl2), xa0, xa1);
+          unpack2(mul2(r2, nl2), xr0, xr1);
+          const f32x2 da = add2(pack2(ex2_approx(xa0), ex2_approx(xa1)), one2);
+          const f32x2 dr = add2(pack2(ex2_approx(xr0), ex2_approx(xr1)), one2);
+          float da0, da1, dr0, dr1;
+          unpack2(da, da0, da1);
+          unpack2(dr, dr0, dr1);
+          unpack2(mul2(a2, pack2(rcp_approx(da0), rcp_approx(da1))), of[0], of[1]);
+          unpack2(mul2(r2, pack2(rcp_approx(dr0), rcp_approx(dr1))), orv[0], orv[1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            float a = bf[c];
+            a = fmaf(wf[c][0], win[0][c], a);
+            a = fmaf(wf[c][1], win[1][c], a);
+            a = fmaf(wf[c][2], win[2][c], a);
+            a = fmaf(wf[c][3], win[3][c], a);
+            of[c] = silu<PRECISE>(a);
+            float r = br[c];
+            r = fmaf(wr[c][0], win[6][c], r);
+            r = fmaf(wr[c][1], win[5][c], r);
+            r = fmaf(wr[c][2], win[4][c], r);
+            r = fmaf(wr[c][3], win[3][c], r);
+            orv[c] = silu<PRECISE>(r);
+          }
         }
         storec<T, CPT>(out_f + (seq_row0 + t) * E + e0, of);
         storec<T, CPT>(out_r + (seq_row0 + t) * E + e0, orv);
