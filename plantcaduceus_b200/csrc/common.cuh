@@ -174,6 +174,36 @@ __device__ __forceinline__ f32x2 exp2_poly2(f32x2 x2) {
   return pack2(p0, p1);
 }
 
+#ifndef PCAD_POLY_DEG
+#define PCAD_POLY_DEG 4
+#endif
+// 2^(d*a) for a pair of products in [-126, 0], entirely on the FMA/ALU pipes, with the multiply folded into the
+// range reduction: r = fma(d, a, 1.5*2^23) rounds the exact product to the nearest integer n, f = fma(d, a, -n) is
+// the exactly-rounded remainder in [-0.5, 0.5]; minimax polynomial for 2^f with p(0) = 1 (degree 4: 2.9e-6 max
+// relative error, degree 3: 1.0e-4); the exponent is inserted by an integer shift-add.  6 (degree 4) packed
+// FMA-pipe instructions more than the MUFU path's one FMUL2, against two MUFU.EX2 saved.
+__device__ __forceinline__ f32x2 exp2_prod_poly2(f32x2 d2, f32x2 a2) {
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f);
+  const f32x2 r2 = fma2(d2, a2, magic);                               // magic + rint(d*a)
+  const f32x2 nn2 = fma2(r2, pack2(-1.0f, -1.0f), magic);             // -rint(d*a)
+  const f32x2 f2 = fma2(d2, a2, nn2);                                 // d*a - rint(d*a)
+#if PCAD_POLY_DEG == 3
+  f32x2 p = fma2(pack2(0.055009059607982635f, 0.055009059607982635f), f2, pack2(0.2422109693288803f, 0.2422109693288803f));
+  p = fma2(p, f2, pack2(0.6932829022407532f, 0.6932829022407532f));
+#else
+  f32x2 p = fma2(pack2(0.009582576341927052f, 0.009582576341927052f), f2, pack2(0.05590682849287987f, 0.05590682849287987f));
+  p = fma2(p, f2, pack2(0.24024106562137604f, 0.24024106562137604f));
+  p = fma2(p, f2, pack2(0.6931241154670715f, 0.6931241154670715f));
+#endif
+  p = fma2(p, f2, pack2(1.0f, 1.0f));
+  float p0, p1, r0, r1;
+  unpack2(p, p0, p1);
+  unpack2(r2, r0, r1);
+  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+  return pack2(p0, p1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -242,6 +272,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// 3D tiled load: coordinates (c0 = innermost element index, c1 = row, c2 = outermost); out-of-range elements
+// (negative or past-the-end coordinates included) are zero-filled and still count towards the barrier's tx bytes.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -383,6 +422,43 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | (0u << 15) | (0u << 16)              // a_major = K, b_major = K
          | (static_cast<uint32_t>(N >> 3) << 17)  // n_dim
          | (static_cast<uint32_t>(M >> 4) << 24); // m_dim
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+
+// 3D row-major [n2][n1][n0] tensor of bf16 or fp32 (n0 contiguous, row pitch ld elements, n2 slices of n1 rows back to
+// back), box = [1][box1][box0], no swizzle, out-of-range elements read as zero.
+inline bool make_tmap_3d(CUtensorMap* map, bool f32, const void* base, long long n0, long long n1, long long n2,
+                         long long ld, int box0, int box1) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t es = f32 ? 4 : 2;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(n0), static_cast<cuuint64_t>(n1), static_cast<cuuint64_t>(n2)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * es, static_cast<cuuint64_t>(ld) * es * static_cast<cuuint64_t>(n1)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box0), static_cast<cuuint32_t>(box1), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
 }
 
 }  // namespace pcad

@@ -38,12 +38,21 @@ constexpr int kScanCH = 128;     // channels per CTA
 constexpr int kScanThreads = 2 * kScanCH;
 constexpr int kScanN = 16;       // d_state
 #ifndef PCAD_SCAN_POLY
-#define PCAD_SCAN_POLY 0
+#define PCAD_SCAN_POLY 1
 #endif
 constexpr int kScanPoly = PCAD_SCAN_POLY;   // pairs (of 8) whose exp2 runs on the FMA pipe
+#ifndef PCAD_SCAN_SPPOLY
+#define PCAD_SCAN_SPPOLY 7   // 0: softplus through MUFU.EX2 + MUFU.LG2; 6 / 7: log2(1 + e) from a polynomial with that many coefficients
+#endif
+#ifndef PCAD_SCAN_UNROLL
+#define PCAD_SCAN_UNROLL 4
+#endif
+constexpr int kScanUnroll = PCAD_SCAN_UNROLL;   // main-loop unroll (2 removes the state-register copies)
 #ifndef PCAD_SCAN_MINBLOCKS
 #define PCAD_SCAN_MINBLOCKS 3
 #endif
+
+template <int V> struct IntTag { static constexpr int value = V; };
 
 template <typename T>
 struct ScanStage {
@@ -56,7 +65,6 @@ template <typename T>
 struct ScanShared {
   ScanStage<T> st[2];
   float bc[2][kScanTC][2 * kScanN];   // fp32 B|C of the chunk being computed
-  float ys[2][kScanTC][kScanCH];      // un-gated outputs of the chunk, per direction
   T pz[2][2][kScanTC][kScanCH];       // [partial | z][direction][step][channel]: prefetched for the chunk epilogue
 };
 
@@ -76,6 +84,7 @@ template <> struct ScanDir<true> {
   // returns d (natural units)
   __device__ __forceinline__ float delta(float raw) const { return softplus<true>(raw + bias); }
   __device__ __forceinline__ float delta_final(float d) const { return d; }
+  template <int NPOLY>
   __device__ __forceinline__ float step(float d, float du, float y0, const float* bc) {
     float y = y0;
 #pragma unroll
@@ -90,25 +99,65 @@ template <> struct ScanDir<true> {
 template <> struct ScanDir<false> {
   f32x2 h[kScanN / 2], a[kScanN / 2];   // a = A (log2 domain: multiplied by d' = d / ln 2)
   float bias_l2;   // bias * log2(e)
+  float dclamp;    // polynomial pairs: d' is clamped so that d' * A >= -126 (2^-126 is 0 for the recurrence)
+  template <int NPOLY>
+  static constexpr __device__ __forceinline__ bool is_poly(int p) {
+    // the first NPOLY pairs of the order 1, 4, 6, 3, 0, 5, 2, 7 (spread over the 8, so that polynomial and MUFU
+    // pairs alternate in the instruction stream)
+    constexpr int order[8] = {1, 4, 6, 3, 0, 5, 2, 7};
+    for (int i = 0; i < NPOLY && i < 8; ++i)
+      if (order[i] == p) return true;
+    return false;
+  }
   __device__ __forceinline__ void init(const float* A, float bias_) {
     bias_l2 = bias_ * kLog2e;
+    float amax = 1e-30f;
 #pragma unroll
     for (int p = 0; p < kScanN / 2; ++p) {
       h[p] = pack2(0.f, 0.f);
       a[p] = A ? pack2(A[2 * p], A[2 * p + 1]) : pack2(0.f, 0.f);
+      if (A) amax = fmaxf(amax, fmaxf(fabsf(A[2 * p]), fabsf(A[2 * p + 1])));
     }
+    dclamp = 126.0f / amax;
   }
   static __device__ __forceinline__ float b_scale() { return kLn2; }   // B is pre-multiplied by ln 2
   // returns d' = softplus(raw + bias) / ln 2  (identity above 20, as the reference)
   __device__ __forceinline__ float delta(float raw) const {
     const float xl = fmaf(raw, kLog2e, bias_l2);
+#if PCAD_SCAN_SPPOLY
+    // log2(1 + 2^x) = max(x, 0) + log2(1 + e), e = 2^-|x| in (0, 1]: one MUFU.EX2, and log2(1 + e) = e q(e) from a
+    // minimax polynomial on the FMA pipe (relative error 1.5e-6 / 8.6e-6 for 7 / 6 coefficients) instead of
+    // MUFU.LG2 -- the scan is bound by the MUFU pipe and the FMA pipe has room.  Above the reference's threshold
+    // (x > 20) the correction is < 2^-28 x, i.e. the identity branch is reproduced to fp32 rounding.
+    const float e = ex2_approx(-fabsf(xl));
+#if PCAD_SCAN_SPPOLY >= 7
+    float q = fmaf(2.035518363e-02f, e, -9.567064047e-02f);
+    q = fmaf(q, e, 2.151583284e-01f);
+    q = fmaf(q, e, -3.390359282e-01f);
+    q = fmaf(q, e, 4.776608944e-01f);
+    q = fmaf(q, e, -7.211598754e-01f);
+    q = fmaf(q, e, 1.442693233e+00f);
+#else
+    float q = fmaf(-3.443166614e-02f, e, 1.460243315e-01f);
+    q = fmaf(q, e, -3.030317128e-01f);
+    q = fmaf(q, e, 4.691744745e-01f);
+    q = fmaf(q, e, -7.204267383e-01f);
+    q = fmaf(q, e, 1.442682981e+00f);
+#endif
+    return fmaf(q, e, fmaxf(xl, 0.0f));
+#else
     const float sp = lg2_approx(1.0f + ex2_approx(xl));
     return xl > 20.0f * kLog2e ? xl : sp;
+#endif
   }
   // delta already softplus'ed (dt_proj's softplus epilogue): only the change of units
   __device__ __forceinline__ float delta_final(float d) const { return d * kLog2e; }
+  template <int NPOLY>
   __device__ __forceinline__ float step(float d, float du, float y0, const float* bc) {
     const f32x2 dd = pack2(d, d), duu = pack2(du, du);
+    float dc = d;
+    if (NPOLY > 0) dc = fminf(d, dclamp);
+    const f32x2 ddc = pack2(dc, dc);
     const ulonglong2* bc2 = reinterpret_cast<const ulonglong2*>(bc);   // 16 bytes = two (n, n+1) pairs
     f32x2 acc[2] = {pack2(y0, 0.f), pack2(0.f, 0.f)};   // two chains: the FFMA2 -> FFMA2 latency is exposed otherwise
 #pragma unroll
@@ -118,16 +167,12 @@ template <> struct ScanDir<false> {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int p = 2 * g + k;
-        const f32x2 x2 = mul2(dd, a[p]);
         f32x2 dA;
-        // the polynomial pairs are spread over the 8: p = 1, 4, 6, 3
-        const bool poly = (kScanPoly >= 1 && p == 1) || (kScanPoly >= 2 && p == 4) || (kScanPoly >= 3 && p == 6) ||
-                          (kScanPoly >= 4 && p == 3);
-        if (poly) {
-          dA = exp2_poly2(x2);
+        if (is_poly<NPOLY>(p)) {
+          dA = exp2_prod_poly2(ddc, a[p]);
         } else {
           float x0, x1;
-          unpack2(x2, x0, x1);
+          unpack2(mul2(dd, a[p]), x0, x1);
           dA = pack2(ex2_approx(x0), ex2_approx(x1));
         }
         h[p] = fma2(dA, h[p], mul2(duu, Bp[k]));
@@ -141,15 +186,29 @@ template <> struct ScanDir<false> {
 };
 
 // DFINAL: delta_* already hold softplus(dt_proj + bias) (the GEMM's softplus epilogue); bias_* are ignored.
+//
+// Staging.  u, delta and B|C of both directions arrive by TMA: six 3-D tensor maps [sequence][row][channel] with a
+// [1][16][128] (B|C: [1][16][32]) box, issued by one thread per chunk into a 2-stage ring and completed on an
+// mbarrier, so the other 255 threads spend no instructions on loads and rows outside [0, L) (ragged last chunk,
+// either direction) are zero-filled by the hardware.  The reverse direction's box holds ascending rows
+// L-16(c+1) .. L-16c-1, i.e. step j of the chunk sits in box row 15-j.  The parked partials and z rows that the
+// chunk epilogue needs are fetched with cp.async (generic proxy: they were written by this CTA's own st.global).
 template <typename T, bool PRECISE, bool DFINAL>
 __global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : PCAD_SCAN_MINBLOCKS)
-biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T* __restrict__ bc_f,
-              const T* __restrict__ u_r, const T* __restrict__ delta_r, const T* __restrict__ bc_r, long long ldbc,
-              int bc_off, const T* __restrict__ z, long long ldz, const float* __restrict__ A_f,
-              const float* __restrict__ D_f, const float* __restrict__ bias_f, const float* __restrict__ A_r,
-              const float* __restrict__ D_r, const float* __restrict__ bias_r, T* y, int L, int E) {
-  extern __shared__ __align__(16) uint8_t scan_smem_raw[];
-  ScanShared<T>& sm = *reinterpret_cast<ScanShared<T>*>(scan_smem_raw);
+biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__ CUtensorMap tm_df,
+              const __grid_constant__ CUtensorMap tm_bcf, const __grid_constant__ CUtensorMap tm_ur,
+              const __grid_constant__ CUtensorMap tm_dr, const __grid_constant__ CUtensorMap tm_bcr,
+              const T* __restrict__ z, long long ldz, const float* __restrict__ A_f, const float* __restrict__ D_f,
+              const float* __restrict__ bias_f, const float* __restrict__ A_r, const float* __restrict__ D_r,
+              const float* __restrict__ bias_r, T* y, int L, int E) {
+  extern __shared__ __align__(128) uint8_t scan_smem_raw[];
+  // TMA destinations must be 128-byte aligned; the runtime only promises 16 for the dynamic segment
+  // (pointer arithmetic on the array itself, so that the accesses stay in the shared address space)
+  ScanShared<T>& sm = *reinterpret_cast<ScanShared<T>*>(scan_smem_raw + ((128u - (smem_u32(scan_smem_raw) & 127u)) & 127u));
+  // Un-gated outputs of the chunk, per direction.  A separate (static) symbol on purpose: the compiler can then
+  // prove that the main loop's stores to it do not alias the loads of later steps and overlaps consecutive steps.
+  __shared__ __align__(16) float ys[2][kScanTC][kScanCH];
+  __shared__ __align__(8) uint64_t full_bar[2];
 
   const int tid = threadIdx.x;
   const int dir = tid >> 7;               // warp-uniform: warps 0-3 forward, 4-7 reverse
@@ -157,37 +216,34 @@ biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T*
   const int e0 = blockIdx.x * kScanCH;
   const int e = e0 + ch;
   const bool active = e < E;
-  const long long row0 = static_cast<long long>(blockIdx.y) * L;
+  const int seq = blockIdx.y;
+  const long long row0 = static_cast<long long>(seq) * L;
   const int nch = (L + kScanTC - 1) / kScanTC;
   constexpr int VEC = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int SEGS = kScanCH / VEC;              // 16-byte segments per 128-channel row
-  constexpr int BCSEGS = 2 * kScanN / VEC;         // 16-byte segments per B|C row
+  constexpr uint32_t kStageBytes = sizeof(ScanStage<T>);
 
-  // chunk c, stage row j: forward timestep 16c + j, reverse timestep L-1-(16c + j).
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_uf); tma_prefetch_desc(&tm_df); tma_prefetch_desc(&tm_bcf);
+    tma_prefetch_desc(&tm_ur); tma_prefetch_desc(&tm_dr); tma_prefetch_desc(&tm_bcr);
+  }
+  __syncthreads();
+
+  // chunk c: forward rows 16c .. 16c+15, reverse rows L-16(c+1) .. L-16c-1 (box row 15-j = step j).  One thread.
   auto issue = [&](int c, int stage) {
     ScanStage<T>& s = sm.st[stage];
-    for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
-      const int dd = idx / (kScanTC * SEGS);
-      const int rem = idx - dd * (kScanTC * SEGS);
-      const int j = rem / SEGS, seg = rem % SEGS;
-      const int i = c * kScanTC + j;
-      const int chn = e0 + seg * VEC;
-      const bool ok = (i < L) && (chn < E);
-      const long long r = row0 + (ok ? (dd ? (L - 1 - i) : i) : 0);
-      const int chs = ok ? chn : 0;
-      const int nb = ok ? 16 : 0;
-      cp_async16(&s.u[dd][j][seg * VEC], (dd ? u_r : u_f) + r * E + chs, nb);
-      cp_async16(&s.d[dd][j][seg * VEC], (dd ? delta_r : delta_f) + r * E + chs, nb);
-    }
-    for (int idx = tid; idx < 2 * kScanTC * BCSEGS; idx += kScanThreads) {
-      const int dd = idx / (kScanTC * BCSEGS);
-      const int rem = idx - dd * (kScanTC * BCSEGS);
-      const int j = rem / BCSEGS, seg = rem % BCSEGS;
-      const int i = c * kScanTC + j;
-      const bool ok = i < L;
-      const long long r = row0 + (ok ? (dd ? (L - 1 - i) : i) : 0);
-      cp_async16(&s.bc_raw[dd][j][seg * VEC], (dd ? bc_r : bc_f) + r * ldbc + bc_off + seg * VEC, ok ? 16 : 0);
-    }
+    uint64_t* bar = &full_bar[stage];
+    mbar_arrive_expect_tx(bar, kStageBytes);
+    const int rf = c * kScanTC, rr = L - (c + 1) * kScanTC;
+    tma_load_3d(&s.u[0][0][0], &tm_uf, bar, e0, rf, seq);
+    tma_load_3d(&s.d[0][0][0], &tm_df, bar, e0, rf, seq);
+    tma_load_3d(&s.bc_raw[0][0][0], &tm_bcf, bar, 0, rf, seq);
+    tma_load_3d(&s.u[1][0][0], &tm_ur, bar, e0, rr, seq);
+    tma_load_3d(&s.d[1][0][0], &tm_dr, bar, e0, rr, seq);
+    tma_load_3d(&s.bc_raw[1][0][0], &tm_bcr, bar, 0, rr, seq);
   };
 
   ScanDir<PRECISE> S;
@@ -199,25 +255,38 @@ biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T*
   const float Dskip = active ? (dir ? D_r : D_f)[e] : 0.f;
   const float bscale = ScanDir<PRECISE>::b_scale();
 
-  issue(0, 0);
-  cp_async_commit();
+  if (tid == 0) issue(0, 0);
   for (int c = 0; c < nch; ++c) {
     const int stage = c & 1;
-    if (c + 1 < nch) {
-      issue(c + 1, stage ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();   // chunk c has landed; the previous chunk's epilogue is done with sm.ys / sm.pz
+    // every thread is past the barrier that followed chunk c-1's main loop: stage^1 is free to be overwritten
+    if (tid == 0 && c + 1 < nch) issue(c + 1, stage ^ 1);
     const ScanStage<T>& s = sm.st[stage];
     const int i0 = c * kScanTC;
     const int nsteps = min(kScanTC, L - i0);
-    // Positions of this chunk that the other direction visited in an EARLIER chunk will be finalised in the
-    // epilogue: fetch their parked partials and z rows now (every earlier epilogue is complete and visible after
-    // the barrier above), so that the epilogue does not wait on global memory.
     const bool has_final = (L - 1 - (i0 + nsteps - 1)) < i0 + nsteps;
+    mbar_wait(&full_bar[stage], (c >> 1) & 1);
+    // B|C to fp32, once per chunk, 4 values per thread (B carries the ln 2 of the log2-domain delta on the fast
+    // path); the reverse direction's rows are un-flipped here so that the main loop indexes both alike
+    {
+      static_assert(2 * kScanTC * 2 * kScanN == 4 * kScanThreads, "one 4-value group per thread");
+      const int dd = tid >> 7, r = tid & 127;
+      const int j = r >> 3, k0 = (r & 7) * 4;
+      const T* src = &s.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
+      float4 v;
+      if constexpr (sizeof(T) == 2) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(src);
+        v.x = __uint_as_float(raw.x << 16); v.y = __uint_as_float(raw.x & 0xffff0000u);
+        v.z = __uint_as_float(raw.y << 16); v.w = __uint_as_float(raw.y & 0xffff0000u);
+      } else {
+        v = *reinterpret_cast<const float4*>(src);
+      }
+      if (k0 < kScanN) { v.x *= bscale; v.y *= bscale; v.z *= bscale; v.w *= bscale; }
+      *reinterpret_cast<float4*>(&sm.bc[dd][j][k0]) = v;
+    }
+    __syncthreads();   // sm.bc is complete; chunk c-1's epilogue (its parked partials, its reads of ys / pz) is done
+    // Positions of this chunk that the other direction visited in an EARLIER chunk will be finalised in the
+    // epilogue: fetch their parked partials and z rows now (every earlier epilogue is complete and visible after the
+    // barrier above), so that the epilogue does not wait on global memory.
     if (has_final) {
       for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
         const int dd = idx / (kScanTC * SEGS);
@@ -233,30 +302,52 @@ biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T*
       }
     }
     cp_async_commit();
-    // B|C to fp32, once per chunk (B carries the ln 2 of the log2-domain delta on the fast path)
-    for (int idx = tid; idx < 2 * kScanTC * 2 * kScanN; idx += kScanThreads) {
-      const int dd = idx / (kScanTC * 2 * kScanN);
-      const int rem = idx - dd * (kScanTC * 2 * kScanN);
-      const int j = rem / (2 * kScanN), k = rem % (2 * kScanN);
-      sm.bc[dd][j][k] = ActT<T>::to_f(s.bc_raw[dd][j][k]) * (k < kScanN ? bscale : 1.0f);
-    }
-    __syncthreads();
 
     if (active) {
-      const T* up = &s.u[dir][0][ch];
-      const T* dp = &s.d[dir][0][ch];
       const float* bcp = &sm.bc[dir][0][0];
-      float* ysp = &sm.ys[dir][0][ch];
+      float* ysp = &ys[dir][0][ch];
+      auto run_chunk = [&](auto rev_tag) {
+        constexpr bool REV = decltype(rev_tag)::value != 0;   // compile-time row order: immediate offsets in the unrolled loop
+        const T* up = &s.u[REV ? 1 : 0][0][ch];
+        const T* dp = &s.d[REV ? 1 : 0][0][ch];
+        auto row = [](int j) { return (REV ? kScanTC - 1 - j : j) * kScanCH; };
+        // softplus runs one step ahead of the recurrence, so its LDS -> EX2 -> polynomial latency chain is off the
+        // critical path of the step that consumes it
+        float uu = ActT<T>::to_f(up[row(0)]);
+        float dl;
+        {
+          const float draw = ActT<T>::to_f(dp[row(0)]);
+          dl = DFINAL ? S.delta_final(draw) : S.delta(draw);
+        }
+        auto advance = [&](int j) -> float {
+          const int jn = min(j + 1, kScanTC - 1);
+          const float uu_n = ActT<T>::to_f(up[row(jn)]);
+          const float draw_n = ActT<T>::to_f(dp[row(jn)]);
+          const float dl_n = DFINAL ? S.delta_final(draw_n) : S.delta(draw_n);
+          const float yv = S.template step<kScanPoly>(dl, dl * uu, Dskip * uu, bcp + j * 2 * kScanN);
+          uu = uu_n;
+          dl = dl_n;
+          return yv;
+        };
+        // blocks of kScanUnroll steps with the stores deferred to the end of the block: no shared-memory store sits
+        // between the loads of consecutive steps, so the scheduler overlaps one step's tail with the next step's head
+        int j = 0;
 #pragma unroll 1
-      for (int j = 0; j < nsteps; ++j) {
-        const float uu = ActT<T>::to_f(up[j * kScanCH]);
-        const float draw = ActT<T>::to_f(dp[j * kScanCH]);
-        const float dl = DFINAL ? S.delta_final(draw) : S.delta(draw);
-        ysp[j * kScanCH] = S.step(dl, dl * uu, Dskip * uu, bcp + j * 2 * kScanN);
-      }
+        for (; j + kScanUnroll <= nsteps; j += kScanUnroll) {
+          float yv[kScanUnroll];
+#pragma unroll
+          for (int k = 0; k < kScanUnroll; ++k) yv[k] = advance(j + k);
+#pragma unroll
+          for (int k = 0; k < kScanUnroll; ++k) ysp[(j + k) * kScanCH] = yv[k];
+        }
+#pragma unroll 1
+        for (; j < nsteps; ++j) ysp[j * kScanCH] = advance(j);
+      };
+      if (dir) run_chunk(IntTag<1>());
+      else run_chunk(IntTag<0>());
     }
     cp_async_wait<0>();
-    __syncthreads();   // both directions' un-gated outputs of the chunk are in sm.ys, partials / z in sm.pz
+    __syncthreads();   // both directions' un-gated outputs of the chunk are in ys, partials / z in sm.pz
 
     // ---- chunk epilogue: 16-byte vectors; item = (direction, step, segment of VEC channels)
     for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
@@ -270,7 +361,7 @@ biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T*
       const int t = dd ? io : i;            // the position itself
       float v[VEC];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) v[k] = sm.ys[dd][j][seg * VEC + k];
+      for (int k = 0; k < VEC; ++k) v[k] = ys[dd][j][seg * VEC + k];
       T* yp = y + (row0 + t) * E + chn;
       if (io >= i0 + nsteps) {              // the other direction comes later: park the partial
         store16<T>(yp, v);
@@ -279,7 +370,7 @@ biscan_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T*
       if (io >= i0) {                       // both visits fall in this chunk: combine from shared memory, once
         if (io > i || (io == i && dd == 1)) continue;   // the later visitor (forward on a tie) writes
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) v[k] += sm.ys[dd ^ 1][io - i0][seg * VEC + k];
+        for (int k = 0; k < VEC; ++k) v[k] += ys[dd ^ 1][io - i0][seg * VEC + k];
       } else {                              // parked in an earlier chunk (by another thread of this CTA)
         float p[VEC];
         load16<T>(&sm.pz[0][dd][j][seg * VEC], p);
@@ -303,14 +394,22 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
                                  const float* D_r, const float* bias_r, T* y, int S, int L, int E,
                                  cudaStream_t stream) {
-  size_t smem = sizeof(ScanShared<T>);
+  size_t smem = sizeof(ScanShared<T>) + 128;   // + alignment slack for the TMA destinations
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static unsigned long long attr_done = 0;
   cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, DFINAL>, static_cast<int>(smem), attr_done);
   if (e1 != cudaSuccess) return e1;
+  constexpr bool f32 = sizeof(T) == 4;
+  CUtensorMap tm[6];
+  const T* act[4] = {u_f, delta_f, u_r, delta_r};
+  bool ok = true;
+  for (int i = 0; i < 4 && ok; ++i) ok = make_tmap_3d(&tm[i], f32, act[i], E, L, S, E, kScanCH, kScanTC);
+  ok = ok && make_tmap_3d(&tm[4], f32, bc_f + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
+  ok = ok && make_tmap_3d(&tm[5], f32, bc_r + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
+  if (!ok) return cudaErrorInvalidValue;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
-  biscan_kernel<T, PRECISE, DFINAL><<<grid, kScanThreads, smem, stream>>>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z,
-                                                                ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E);
+  biscan_kernel<T, PRECISE, DFINAL><<<grid, kScanThreads, smem, stream>>>(tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], z, ldz, A_f,
+                                                                D_f, bias_f, A_r, D_r, bias_r, y, L, E);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,106 @@
+// Microbenchmark: the selective-scan inner step (ScanDir<false>::step<NPOLY> of csrc/scan.cuh) in isolation --
+// no global traffic, no chunk phases, no barriers -- for MUFU-flavoured warps, polynomial-flavoured warps and mixes.
+// Reports SMSP cycles per warp-step (from clock64), to be compared with the pipe model (8 cyc per MUFU, 2 per FFMA2).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -I plantcaduceus_b200/csrc \
+//        -o tools/ub/scan_step tools/ub/scan_step.cu
+#include <cstdio>
+#include "scan.cuh"
+using namespace pcad;
+#ifndef UB_BC_CONST
+#define UB_BC_CONST 0   // 1: B|C rows come from __constant__ memory instead of shared memory (no LDS.128 in the step)
+#endif
+__constant__ __align__(16) float c_bc[16][32];
+
+template <int NL, int NH, int WARPS, bool SOFTPLUS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k(float* out, long long* cyc, int iters, int mod, int thr) {
+  __shared__ __align__(16) float bc[16][32];
+  __shared__ __align__(16) float ys[4][WARPS * 32];
+  __shared__ __nv_bfloat16 dsm[16][256], usm[16][256];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16 * 32; i += blockDim.x) bc[i / 32][i % 32] = 0.01f * ((i * 7) % 13) - 0.05f;
+  for (int j = 0; j < 16; ++j) {
+    if (tid < 256) dsm[j][tid] = __float2bfloat16(0.1f * ((tid + j) % 7) - 0.3f);
+    if (tid < 256) usm[j][tid] = __float2bfloat16(0.2f * ((tid * 3 + j) % 5) - 0.4f);
+  }
+  float A[16];
+  for (int n = 0; n < 16; ++n) A[n] = -(n + 1.0f) * (1.0f + 1e-4f * (tid % 97)) * kLog2e;
+  ScanDir<false> S;
+  S.init(A, -4.0f);
+  const bool heavy = mod > 0 && (warp % mod) < thr;
+  __syncthreads();
+  const long long t0 = clock64();
+  auto run = [&](auto tag) {
+    constexpr int NP = decltype(tag)::value;
+    float uu = __bfloat162float(usm[0][tid & 255]);
+    float dl = SOFTPLUS ? S.delta(__bfloat162float(dsm[0][tid & 255])) : S.delta_final(__bfloat162float(dsm[0][tid & 255]));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+      for (int j = 0; j < 16; j += 4) {
+        float yv[4];
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const int jn = (j + k2 + 1) & 15;
+          const float uu_n = __bfloat162float(usm[jn][tid & 255]);
+          const float dr = __bfloat162float(dsm[jn][tid & 255]);
+          const float dl_n = SOFTPLUS ? S.delta(dr) : S.delta_final(dr);
+          yv[k2] = S.template step<NP>(dl, dl * uu, 0.5f * uu, UB_BC_CONST ? &c_bc[j + k2][0] : &bc[j + k2][0]);
+          uu = uu_n; dl = dl_n;
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) ys[k2][tid] = yv[k2];
+      }
+    }
+  };
+  if (heavy) run(IntTag<NH>()); else run(IntTag<NL>());
+  const long long t1 = clock64();
+  __syncthreads();
+  if (tid == 0) cyc[blockIdx.x] = t1 - t0;   // warp 0's span; all warps run the same number of steps
+  float acc = 0;
+  for (int j = 0; j < 4; ++j) acc += ys[j][tid];
+  if (acc == 12345.678f) out[0] = acc;
+}
+
+template <int NL, int NH, int WARPS, bool SOFTPLUS>
+void run(const char* name, int mod, int thr) {
+  cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
+  const int blocks = pr.multiProcessorCount;
+  float* out; long long* cyc; cudaMalloc(&out, 4); cudaMalloc(&cyc, blocks * 8);
+  const int iters = 400;   // x16 steps
+  k<NL, NH, WARPS, SOFTPLUS><<<blocks, WARPS * 32>>>(out, cyc, 10, mod, thr);
+  cudaDeviceSynchronize();
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  k<NL, NH, WARPS, SOFTPLUS><<<blocks, WARPS * 32>>>(out, cyc, iters, mod, thr);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  cudaError_t err = cudaGetLastError();
+  long long* h = new long long[blocks]; cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < blocks; ++i) avg += h[i]; avg /= blocks;
+  const double steps_per_smsp = 16.0 * iters * WARPS / 4.0;
+  printf("%-34s warps/SM=%2d light=%d heavy=%d mix=%d/%d softplus=%d : %7.1f cyc per warp-step per SMSP  (%.3f ms, %s)\n", name, WARPS,
+         NL, NH, thr, mod, (int)SOFTPLUS, avg / steps_per_smsp, ms, cudaGetErrorString(err));
+  cudaFree(out); cudaFree(cyc); delete[] h;
+}
+
+int main() {
+  printf("PCAD_SCAN_SPPOLY=%d PCAD_POLY_DEG=%d UB_BC_CONST=%d\n", PCAD_SCAN_SPPOLY, PCAD_POLY_DEG, UB_BC_CONST);
+  {
+    float hbc[16][32];
+    for (int i = 0; i < 512; ++i) hbc[i / 32][i % 32] = 0.01f * ((i * 7) % 13) - 0.05f;
+    cudaMemcpyToSymbol(c_bc, hbc, sizeof(hbc));
+  }
+  run<0, 8, 24, true>("all MUFU", 0, 0);
+  run<0, 8, 24, false>("all MUFU, no softplus", 0, 0);
+  run<1, 8, 24, true>("1 poly pair in every warp", 0, 0);
+  run<2, 8, 24, true>("2 poly pairs in every warp", 0, 0);
+  run<3, 8, 24, true>("3 poly pairs in every warp", 0, 0);
+  run<0, 8, 24, true>("all polynomial", 1, 1);
+  run<0, 8, 24, true>("1 of 5 warps polynomial", 5, 1);
+  run<0, 6, 24, true>("1 of 3 warps 6-pair polynomial", 3, 1);
+  run<0, 4, 24, true>("3 of 7 warps 4-pair", 7, 3);
+  run<1, 4, 24, true>("1 pair everywhere, 3 of 7 warps 4-pair", 7, 3);
+  run<1, 3, 24, true>("1 pair everywhere, 3 of 7 warps 3-pair", 7, 3);
+  run<0, 8, 16, true>("all MUFU, 16 warps", 0, 0);
+  run<1, 8, 16, true>("1 poly pair, 16 warps", 0, 0);
+  return 0;
+}
