@@ -60,6 +60,118 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k(float* out, long long* cyc, i
   if (acc == 12345.678f) out[0] = acc;
 }
 
+// ScanDir<false>::step() split in two for software pipelining: exps() only produces the 8 pair-decays of a step (all of
+// its MUFU work), consume() only does the FMA-pipe work; the caller issues exps() of step j+1 before consume() of step j.
+template <int NPOLY>
+__device__ __forceinline__ void exps(const ScanDir<false>& S, float d, f32x2 (&dA)[kScanN / 2]) {
+  const f32x2 dd = pack2(d, d);
+  float dc = d;
+  if (NPOLY > 0) dc = fminf(d, S.dclamp);
+  const f32x2 ddc = pack2(dc, dc);
+#pragma unroll
+  for (int p = 0; p < kScanN / 2; ++p) {
+    if (ScanDir<false>::is_poly<NPOLY>(p)) {
+      dA[p] = exp2_prod_poly2(ddc, S.a[p]);
+    } else {
+      float x0, x1;
+      unpack2(mul2(dd, S.a[p]), x0, x1);
+      dA[p] = pack2(ex2_approx(x0), ex2_approx(x1));
+    }
+  }
+}
+__device__ __forceinline__ float consume(ScanDir<false>& S, const f32x2 (&dA)[kScanN / 2], float du, float y0, const float* bc) {
+  const f32x2 duu = pack2(du, du);
+  const ulonglong2* bc2 = reinterpret_cast<const ulonglong2*>(bc);
+  f32x2 acc[2] = {pack2(y0, 0.f), pack2(0.f, 0.f)};
+#pragma unroll
+  for (int g = 0; g < kScanN / 4; ++g) {
+    const ulonglong2 Bq = bc2[g], Cq = bc2[kScanN / 4 + g];
+    const f32x2 Bp[2] = {Bq.x, Bq.y}, Cp[2] = {Cq.x, Cq.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int p = 2 * g + k;
+      S.h[p] = fma2(dA[p], S.h[p], mul2(duu, Bp[k]));
+      acc[k] = fma2(S.h[p], Cp[k], acc[k]);
+    }
+  }
+  float s0, s1;
+  unpack2(add2(acc[0], acc[1]), s0, s1);
+  return s0 + s1;
+}
+
+// software-pipelined variant: MUFU work of step j+1 is issued before the FMA work of step j (16 more registers)
+template <int NP, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) kp(float* out, long long* cyc, int iters) {
+  __shared__ __align__(16) float bc[16][32];
+  __shared__ __align__(16) float ys[4][WARPS * 32];
+  __shared__ __nv_bfloat16 dsm[16][256], usm[16][256];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 16 * 32; i += blockDim.x) bc[i / 32][i % 32] = 0.01f * ((i * 7) % 13) - 0.05f;
+  for (int j = 0; j < 16; ++j) {
+    if (tid < 256) dsm[j][tid] = __float2bfloat16(0.1f * ((tid + j) % 7) - 0.3f);
+    if (tid < 256) usm[j][tid] = __float2bfloat16(0.2f * ((tid * 3 + j) % 5) - 0.4f);
+  }
+  float A[16];
+  for (int n = 0; n < 16; ++n) A[n] = -(n + 1.0f) * (1.0f + 1e-4f * (tid % 97)) * kLog2e;
+  ScanDir<false> S;
+  S.init(A, -4.0f);
+  __syncthreads();
+  const long long t0 = clock64();
+  float uu = __bfloat162float(usm[0][tid & 255]);
+  float dl = S.delta(__bfloat162float(dsm[0][tid & 255]));
+  float dl1 = S.delta(__bfloat162float(dsm[1][tid & 255]));
+  f32x2 dA[8];
+  exps<NP>(S, dl, dA);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+    for (int j = 0; j < 16; j += 4) {
+      float yv[4];
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        const int jn = (j + k2 + 1) & 15, jn2 = (j + k2 + 2) & 15;
+        const float uu_n = __bfloat162float(usm[jn][tid & 255]);
+        const float dl2 = S.delta(__bfloat162float(dsm[jn2][tid & 255]));
+        f32x2 dAn[8];
+        exps<NP>(S, dl1, dAn);
+        yv[k2] = consume(S, dA, dl * uu, 0.5f * uu, &bc[j + k2][0]);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) dA[p] = dAn[p];
+        uu = uu_n; dl = dl1; dl1 = dl2;
+      }
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) ys[k2][tid] = yv[k2];
+    }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+  float acc = 0;
+  for (int j = 0; j < 4; ++j) acc += ys[j][tid];
+  if (acc == 12345.678f) out[0] = acc;
+}
+
+template <int NP, int WARPS, int MINB>
+void runp(const char* name) {
+  cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
+  const int blocks = pr.multiProcessorCount * MINB;
+  float* out; long long* cyc; cudaMalloc(&out, 4); cudaMalloc(&cyc, blocks * 8);
+  const int iters = 400;
+  kp<NP, WARPS, MINB><<<blocks, WARPS * 32>>>(out, cyc, 10);
+  cudaDeviceSynchronize();
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  kp<NP, WARPS, MINB><<<blocks, WARPS * 32>>>(out, cyc, iters);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  cudaError_t err = cudaGetLastError();
+  long long* h = new long long[blocks]; cudaMemcpy(h, cyc, blocks * 8, cudaMemcpyDeviceToHost);
+  double avg = 0; for (int i = 0; i < blocks; ++i) avg += h[i]; avg /= blocks;
+  const double steps_per_smsp = 16.0 * iters * WARPS * MINB / 4.0;
+  printf("%-34s warps/SM=%2d poly=%d pipelined : %7.1f cyc per warp-step per SMSP  (%.3f ms, %s)\n", name, WARPS * MINB, NP,
+         avg / steps_per_smsp, ms, cudaGetErrorString(err));
+  cudaFree(out); cudaFree(cyc); delete[] h;
+}
+
 template <int NL, int NH, int WARPS, bool SOFTPLUS>
 void run(const char* name, int mod, int thr) {
   cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
@@ -100,6 +212,15 @@ int main() {
   run<0, 4, 24, true>("3 of 7 warps 4-pair", 7, 3);
   run<1, 4, 24, true>("1 pair everywhere, 3 of 7 warps 4-pair", 7, 3);
   run<1, 3, 24, true>("1 pair everywhere, 3 of 7 warps 3-pair", 7, 3);
+  runp<0, 16, 1>("pipelined, 16 warps (128 regs)");
+  runp<1, 16, 1>("pipelined, 16 warps (128 regs)");
+  runp<2, 16, 1>("pipelined, 16 warps (128 regs)");
+  runp<0, 8, 2>("pipelined, 2 x 8 warps (128 regs)");
+  runp<1, 8, 2>("pipelined, 2 x 8 warps (128 regs)");
+  runp<0, 20, 1>("pipelined, 20 warps (96 regs)");
+  runp<1, 20, 1>("pipelined, 20 warps (96 regs)");
+  runp<0, 24, 1>("pipelined, 24 warps (80 regs)");
+  runp<1, 24, 1>("pipelined, 24 warps (80 regs)");
   run<0, 8, 16, true>("all MUFU, 16 warps", 0, 0);
   run<1, 8, 16, true>("1 poly pair, 16 warps", 0, 0);
   return 0;
