@@ -164,6 +164,7 @@ add_rmsnorm_kernel(const T* __restrict__ x, const RT* __restrict__ res_in, const
 // out_r[t] = SiLU(b_r + sum_k w_r[k] x[t+3-k])  (the causal conv of the time-reversed sequence).
 constexpr int kConvTT = 64;   // timesteps per thread (halo re-read: 6 / 64)
 constexpr int kConvBlk = 8;   // rows fetched per batch of back-to-back loads
+template <int V> struct ConvTag { static constexpr int value = V; };
 
 // CPT channels per thread as loaded from memory
 template <typename T, int CPT> struct RawC;
@@ -217,81 +218,95 @@ conv_silu_kernel(const T* __restrict__ x, long long ldx, const float* __restrict
     bf[c] = b_f[e0 + c];
     br[c] = b_r[e0 + c];
   }
-  const T* xcol = x + e0;
+  // Addressing: one 64-bit base per tensor and thread (row t0 of this sequence, this thread's channels) and 32-bit
+  // element offsets that advance by a constant per step, so a step costs one IMAD.WIDE per access instead of a
+  // 64-bit row * pitch product; blocks whose rows t0-3 .. t0+kConvTT+2 all lie inside the sequence (INTERIOR) skip
+  // every bounds check.
+  const T* xb = x + (seq_row0 + t0) * ldx + e0;
+  T* ofb = out_f + (seq_row0 + t0) * E + e0;
+  T* orb = out_r + (seq_row0 + t0) * E + e0;
+  const int ldxi = static_cast<int>(ldx);
   raw_t zero_raw;
   memset(&zero_raw, 0, sizeof(zero_raw));
-  auto fetch = [&](int t) -> raw_t {   // row t of this sequence, zero outside [0, L)
-    return (t >= 0 && t < L) ? *reinterpret_cast<const raw_t*>(xcol + (seq_row0 + t) * ldx) : zero_raw;
-  };
-  // win[j] holds x[t - 3 + j], j = 0..6, for the step being computed
-  float win[7][CPT];
-  raw_t nxt[kConvBlk];
+  auto body = [&](auto interior_tag) {
+    constexpr bool INTERIOR = decltype(interior_tag)::value != 0;
+    auto fetch = [&](int dt) -> raw_t {   // row t0 + dt of this sequence, zero outside [0, L)
+      if (INTERIOR || (t0 + dt >= 0 && t0 + dt < L)) return *reinterpret_cast<const raw_t*>(xb + dt * ldxi);
+      return zero_raw;
+    };
+    // win[j] holds x[t - 3 + j], j = 0..6, for the step being computed
+    float win[7][CPT];
+    raw_t nxt[kConvBlk];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) cvtc(fetch(t0 - 3 + j), win[j]);
+    for (int j = 0; j < 6; ++j) cvtc(fetch(j - 3), win[j]);
 #pragma unroll
-  for (int i = 0; i < kConvBlk; ++i) nxt[i] = fetch(t0 + 3 + i);
+    for (int i = 0; i < kConvBlk; ++i) nxt[i] = fetch(3 + i);
+    int ooff = 0;   // element offset of the output row being written
 #pragma unroll 1
-  for (int blk = 0; blk < kConvTT; blk += kConvBlk) {
-    if (t0 + blk >= L) break;
-    raw_t cur[kConvBlk];
+    for (int blk = 0; blk < kConvTT; blk += kConvBlk) {
+      if (!INTERIOR && t0 + blk >= L) break;
+      raw_t cur[kConvBlk];
 #pragma unroll
-    for (int i = 0; i < kConvBlk; ++i) cur[i] = nxt[i];
-    if (blk + kConvBlk < kConvTT) {   // next batch of rows: in flight while this batch is computed
+      for (int i = 0; i < kConvBlk; ++i) cur[i] = nxt[i];
+      if (blk + kConvBlk < kConvTT) {   // next batch of rows: in flight while this batch is computed
 #pragma unroll
-      for (int i = 0; i < kConvBlk; ++i) nxt[i] = fetch(t0 + blk + kConvBlk + 3 + i);
-    }
-#pragma unroll
-    for (int i = 0; i < kConvBlk; ++i) {
-      const int t = t0 + blk + i;
-      cvtc(cur[i], win[6]);
-      if (t < L) {
-        float of[CPT], orv[CPT];
-        if constexpr (!PRECISE && CPT == 2) {
-          // bf16 fast path: the two channels of a thread ride in one fp32x2 register pair (FFMA2 / FMUL2 / FADD2: half
-          // the issue slots), so the kernel is left with its MUFU work (ex2 + rcp per output) and its HBM traffic
-          f32x2 a2 = pack2(bf[0], bf[1]), r2 = pack2(br[0], br[1]);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            a2 = fma2(pack2(wf[0][k], wf[1][k]), pack2(win[k][0], win[k][1]), a2);
-            r2 = fma2(pack2(wr[0][k], wr[1][k]), pack2(win[6 - k][0], win[6 - k][1]), r2);
-          }
-          const f32x2 nl2 = pack2(-kLog2e, -kLog2e), one2 = pack2(1.0f, 1.0f);
-          float xa0, xa1, xr0, xr1;
-          unpack2(mul2(a2, nl2), xa0, xa1);
-          unpack2(mul2(r2, nl2), xr0, xr1);
-          const f32x2 da = add2(pack2(ex2_approx(xa0), ex2_approx(xa1)), one2);
-          const f32x2 dr = add2(pack2(ex2_approx(xr0), ex2_approx(xr1)), one2);
-          float da0, da1, dr0, dr1;
-          unpack2(da, da0, da1);
-          unpack2(dr, dr0, dr1);
-          unpack2(mul2(a2, pack2(rcp_approx(da0), rcp_approx(da1))), of[0], of[1]);
-          unpack2(mul2(r2, pack2(rcp_approx(dr0), rcp_approx(dr1))), orv[0], orv[1]);
-        } else {
-#pragma unroll
-          for (int c = 0; c < CPT; ++c) {
-            float a = bf[c];
-            a = fmaf(wf[c][0], win[0][c], a);
-            a = fmaf(wf[c][1], win[1][c], a);
-            a = fmaf(wf[c][2], win[2][c], a);
-            a = fmaf(wf[c][3], win[3][c], a);
-            of[c] = silu<PRECISE>(a);
-            float r = br[c];
-            r = fmaf(wr[c][0], win[6][c], r);
-            r = fmaf(wr[c][1], win[5][c], r);
-            r = fmaf(wr[c][2], win[4][c], r);
-            r = fmaf(wr[c][3], win[3][c], r);
-            orv[c] = silu<PRECISE>(r);
-          }
-        }
-        storec<T, CPT>(out_f + (seq_row0 + t) * E + e0, of);
-        storec<T, CPT>(out_r + (seq_row0 + t) * E + e0, orv);
+        for (int i = 0; i < kConvBlk; ++i) nxt[i] = fetch(blk + kConvBlk + 3 + i);
       }
 #pragma unroll
-      for (int j = 0; j < 6; ++j)
+      for (int i = 0; i < kConvBlk; ++i) {
+        cvtc(cur[i], win[6]);
+        if (INTERIOR || t0 + blk + i < L) {
+          float of[CPT], orv[CPT];
+          if constexpr (!PRECISE && CPT == 2) {
+            // bf16 fast path: the two channels of a thread ride in one fp32x2 register pair (FFMA2 / FMUL2 / FADD2: half
+            // the issue slots), so the kernel is left with its MUFU work (ex2 + rcp per output) and its HBM traffic
+            f32x2 a2 = pack2(bf[0], bf[1]), r2 = pack2(br[0], br[1]);
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) win[j][c] = win[j + 1][c];
+            for (int k = 0; k < 4; ++k) {
+              a2 = fma2(pack2(wf[0][k], wf[1][k]), pack2(win[k][0], win[k][1]), a2);
+              r2 = fma2(pack2(wr[0][k], wr[1][k]), pack2(win[6 - k][0], win[6 - k][1]), r2);
+            }
+            const f32x2 nl2 = pack2(-kLog2e, -kLog2e), one2 = pack2(1.0f, 1.0f);
+            float xa0, xa1, xr0, xr1;
+            unpack2(mul2(a2, nl2), xa0, xa1);
+            unpack2(mul2(r2, nl2), xr0, xr1);
+            const f32x2 da = add2(pack2(ex2_approx(xa0), ex2_approx(xa1)), one2);
+            const f32x2 dr = add2(pack2(ex2_approx(xr0), ex2_approx(xr1)), one2);
+            float da0, da1, dr0, dr1;
+            unpack2(da, da0, da1);
+            unpack2(dr, dr0, dr1);
+            unpack2(mul2(a2, pack2(rcp_approx(da0), rcp_approx(da1))), of[0], of[1]);
+            unpack2(mul2(r2, pack2(rcp_approx(dr0), rcp_approx(dr1))), orv[0], orv[1]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+              float a = bf[c];
+              a = fmaf(wf[c][0], win[0][c], a);
+              a = fmaf(wf[c][1], win[1][c], a);
+              a = fmaf(wf[c][2], win[2][c], a);
+              a = fmaf(wf[c][3], win[3][c], a);
+              of[c] = silu<PRECISE>(a);
+              float r = br[c];
+              r = fmaf(wr[c][0], win[6][c], r);
+              r = fmaf(wr[c][1], win[5][c], r);
+              r = fmaf(wr[c][2], win[4][c], r);
+              r = fmaf(wr[c][3], win[3][c], r);
+              orv[c] = silu<PRECISE>(r);
+            }
+          }
+          storec<T, CPT>(ofb + ooff, of);
+          storec<T, CPT>(orb + ooff, orv);
+        }
+        ooff += E;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) win[j][c] = win[j + 1][c];
+      }
     }
-  }
+  };
+  if (t0 >= 3 && t0 + kConvTT + 3 <= L) body(ConvTag<1>());
+  else body(ConvTag<0>());
 }
 
 // ---- RC LM head [EXT RCPSLMHead.forward + .float()] ---------------------------------------------
