@@ -350,6 +350,51 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     __syncthreads();   // both directions' un-gated outputs of the chunk are in ys, partials / z in sm.pz
 
     // ---- chunk epilogue: 16-byte vectors; item = (direction, step, segment of VEC channels)
+    if constexpr (!PRECISE && sizeof(T) == 2) {
+      // bf16 fast paths for the two block-uniform cases (every chunk of an even-length sequence): all items of
+      // the chunk park ("early": the other direction comes in a later chunk) or all finalise from a partial parked
+      // in an earlier chunk ("late").  No per-item branching, packed fp32x2 arithmetic for the add and the gate.
+      const bool early = !has_final, late = (L - 1 - i0) < i0;
+      if (early || late) {
+        static_assert(kScanTC * (kScanCH / 8) == kScanThreads, "one item per thread and direction");
+        const int j = tid >> 4, seg = tid & 15;
+        const int chn = e0 + seg * 8;
+        if (j < nsteps && chn < E) {
+#pragma unroll
+          for (int dd = 0; dd < 2; ++dd) {
+            const int i = i0 + j;
+            const int t = dd ? L - 1 - i : i;
+            const float4 a = *reinterpret_cast<const float4*>(&ys[dd][j][seg * 8]);
+            const float4 b = *reinterpret_cast<const float4*>(&ys[dd][j][seg * 8 + 4]);
+            f32x2 v2[4] = {pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w)};
+            if (late) {
+              const uint4 pr = *reinterpret_cast<const uint4*>(&sm.pz[0][dd][j][seg * 8]);
+              const uint4 zr = *reinterpret_cast<const uint4*>(&sm.pz[1][dd][j][seg * 8]);
+              const uint32_t pw[4] = {pr.x, pr.y, pr.z, pr.w}, zw[4] = {zr.x, zr.y, zr.z, zr.w};
+              const f32x2 nl2 = pack2(-kLog2e, -kLog2e), one2 = pack2(1.0f, 1.0f);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const f32x2 p2 = pack2(__uint_as_float(pw[q] << 16), __uint_as_float(pw[q] & 0xffff0000u));
+                const f32x2 z2 = pack2(__uint_as_float(zw[q] << 16), __uint_as_float(zw[q] & 0xffff0000u));
+                float x0, x1, d0, d1;
+                unpack2(mul2(z2, nl2), x0, x1);
+                unpack2(add2(pack2(ex2_approx(x0), ex2_approx(x1)), one2), d0, d1);
+                const f32x2 g2 = mul2(z2, pack2(rcp_approx(d0), rcp_approx(d1)));   // SiLU(z)
+                v2[q] = mul2(add2(v2[q], p2), g2);
+              }
+            }
+            uint4 out;
+            float lo, hi;
+            unpack2(v2[0], lo, hi); out.x = pack_bf16x2(lo, hi);
+            unpack2(v2[1], lo, hi); out.y = pack_bf16x2(lo, hi);
+            unpack2(v2[2], lo, hi); out.z = pack_bf16x2(lo, hi);
+            unpack2(v2[3], lo, hi); out.w = pack_bf16x2(lo, hi);
+            *reinterpret_cast<uint4*>(y + (row0 + t) * E + chn) = out;
+          }
+        }
+        continue;
+      }
+    }
     for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
       const int dd = idx / (kScanTC * SEGS);
       const int rem = idx - dd * (kScanTC * SEGS);
