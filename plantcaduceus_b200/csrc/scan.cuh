@@ -287,7 +287,19 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     // Positions of this chunk that the other direction visited in an EARLIER chunk will be finalised in the
     // epilogue: fetch their parked partials and z rows now (every earlier epilogue is complete and visible after the
     // barrier above), so that the epilogue does not wait on global memory.
-    if (has_final) {
+    const bool late_chunk = (L - 1 - i0) < i0;   // every position of the chunk was parked in an earlier chunk
+    if (sizeof(T) == 2 && late_chunk) {
+      // block-uniform fast path (bf16): one (step, segment) item per thread and direction, no per-item classification
+      const int j = tid >> 4, seg = tid & 15;
+      const int chn = e0 + seg * 8;
+      if (j < nsteps && chn < E) {
+        const long long rf = row0 + i0 + j, rr = row0 + (L - 1 - i0 - j);
+        cp_async16(&sm.pz[0][0][j][seg * 8], y + rf * E + chn, 16);
+        cp_async16(&sm.pz[1][0][j][seg * 8], z + rf * ldz + chn, 16);
+        cp_async16(&sm.pz[0][1][j][seg * 8], y + rr * E + chn, 16);
+        cp_async16(&sm.pz[1][1][j][seg * 8], z + rr * ldz + chn, 16);
+      }
+    } else if (has_final) {
       for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
         const int dd = idx / (kScanTC * SEGS);
         const int rem = idx - dd * (kScanTC * SEGS);
@@ -354,7 +366,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
       // bf16 fast paths for the two block-uniform cases (every chunk of an even-length sequence): all items of
       // the chunk park ("early": the other direction comes in a later chunk) or all finalise from a partial parked
       // in an earlier chunk ("late").  No per-item branching, packed fp32x2 arithmetic for the add and the gate.
-      const bool early = !has_final, late = (L - 1 - i0) < i0;
+      const bool early = !has_final, late = late_chunk;
       if (early || late) {
         static_assert(kScanTC * (kScanCH / 8) == kScanThreads, "one item per thread and direction");
         const int j = tid >> 4, seg = tid & 15;
