@@ -10,18 +10,32 @@
 // coefficients in registers.  (Keeping both directions in one thread needs ~126 registers, i.e. 4 warps per
 // scheduler, and the kernel is latency-bound there; one direction per thread fits 6 warps per scheduler.)
 // Step i advances the forward scan at t_f = i and the reverse scan at t_r = L-1-i.  Inputs are streamed in chunks
-// of 16 steps through a 2-stage cp.async ring; the 32 B/C values per step are converted to fp32 once per chunk
-// and broadcast-read.  Each thread leaves its un-gated y for the chunk in shared memory; a vectorised chunk
-// epilogue then either parks the partial in y (the other direction has not reached that position yet) or adds the
-// other direction's parked partial, applies SiLU(z) and stores the final value -- 16-byte global accesses only.
+// of 16 steps by TMA (3-D tensor maps, one issuing thread, 2-stage mbarrier ring: see biscan_kernel); the 32 B/C
+// values per step are converted to fp32 once per chunk and broadcast-read.  Each thread leaves its un-gated y for
+// the chunk in shared memory; a vectorised chunk epilogue then either parks the partial in y (the other direction
+// has not reached that position yet) or adds the other direction's parked partial, applies SiLU(z) and stores the
+// final value -- 16-byte global accesses only.
 //
-// The bf16 kernel is bound by the MUFU (ex2) and FMA pipes, not by HBM (ncu: profiles/).  Its inner loop
-// (a) keeps (n, n+1) state pairs in 64-bit registers and uses the packed fp32x2 instructions of sm_100
-// (FFMA2 / FMUL2: two lanes per issue slot), (b) can take kScanPoly of the 8 pair-exponentials from an FMA-pipe
-// polynomial instead of MUFU.EX2 (default 0: measured on B200 at l32, B = 256: 0 -> 5.56 ms, 1 -> 5.57, 2 -> 5.91,
-// 3 -> 6.34 per launch -- a polynomial exp costs as many FMA-pipe cycles as the MUFU cycles it saves and the two
-// pipes share issue slots), (c) works in the log2 domain end to end: d' = log2(1 + 2^((delta + bias) log2 e)),
-// exp(d A) = 2^(d' A), and the ln 2 that d = d' ln 2 owes to the input term is folded into B when B is converted.
+// The bf16 kernel is bound by the MUFU pipe (16 ex2 / clk / SM) and by instruction issue together, not by HBM (ncu:
+// profiles/; tools/ub/scan_step.cu isolates the step).  What the kernel does about it:
+// (a) (n, n+1) state pairs live in 64-bit registers and use the packed fp32x2 instructions of sm_100 (FFMA2 /
+//     FMUL2: two lanes per issue slot);
+// (b) everything is in the log2 domain: d' = log2(1 + 2^((delta + bias) log2 e)), exp(d A) = 2^(d' A), and the ln 2
+//     that d = d' ln 2 owes to the input term is folded into B when B is converted;
+// (c) softplus costs one MUFU op, not two: log2(1 + e), e = 2^-|x| in (0, 1], is a 7-coefficient FMA-pipe polynomial
+//     (PCAD_SCAN_SPPOLY), and it runs one step ahead of the recurrence;
+// (d) the main loop advances in blocks of 4 steps whose shared-memory stores are deferred to the end of the block, so
+//     the scheduler overlaps one step's tail with the next step's loads (and the state-register copies of a 1-step
+//     loop disappear);
+// (e) every instruction outside the main loop counts (the kernel issues at ~0.65 IPC): loads are TMA, the B|C
+//     conversion is one 4-value group per thread, the epilogue and the prefetch of parked partials have branch-free
+//     block-uniform fast paths;
+// (f) kScanPoly of the 8 pair-exponentials can come from an FMA-pipe polynomial with the multiply folded into the
+//     range reduction (exp2_prod_poly2) instead of MUFU.EX2.  Default 0.  Measured at l32, B = 256 with the final
+//     kernel structure: 0 -> 5.08 ms per launch, 1 -> 5.11, 2 -> 5.33; packed FFMA2 with three distinct operands
+//     runs at ~2.7 cycles, so a polynomial pair costs more issue/FMA time than the MUFU time it frees
+//     (profiles/r01_scan_step_ub.txt).  Giving whole warps a polynomial flavour, a software-pipelined step and an
+//     in-loop park/finalise (no epilogue phase) were also built and measured: none beat this configuration.
 #pragma once
 
 #include <stdlib.h>
@@ -38,7 +52,7 @@ constexpr int kScanCH = 128;     // channels per CTA
 constexpr int kScanThreads = 2 * kScanCH;
 constexpr int kScanN = 16;       // d_state
 #ifndef PCAD_SCAN_POLY
-#define PCAD_SCAN_POLY 1
+#define PCAD_SCAN_POLY 0
 #endif
 constexpr int kScanPoly = PCAD_SCAN_POLY;   // pairs (of 8) whose exp2 runs on the FMA pipe
 #ifndef PCAD_SCAN_SPPOLY
