@@ -278,12 +278,12 @@ def run_ours(args):
     scan_bytes_per_launch = SCAN_MB_PER_WINDOW[args.model] * 1e6 * B / cfg.n_layer
     scan_gbs = scan_bytes_per_launch / (scan_launch_ms * 1e-3) / 1e9
     # MUFU view of the same kernel, counting the special-function ops it EXECUTES per (step, channel, direction):
-    # 14 ex2 for the decays (the 15th and 16th come from the FMA-pipe polynomial), 1 ex2 for softplus (its log2(1+e)
-    # is a polynomial too) and 1 for the gate (ex2 + rcp per output, shared by the two directions) = 16/16 of the
-    # state-update count, against 16 MUFU lanes / clk / SM (measured: tools/ub/fma_pipes.cu) at the observed clock
+    # 16 ex2 for the decays, 1 ex2 for softplus (its log2(1+e) is an FMA-pipe polynomial) and 1 for the gate (ex2 + rcp
+    # per output, shared by the two directions) = 18/16 of the state-update count, against 16 MUFU lanes / clk / SM
+    # (measured: tools/ub/fma_pipes.cu) at the observed clock
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     mufu_peak = 16.0 * 148 * sm_mhz * 1e6
-    mufu_ops = SCAN_GEXP_PER_WINDOW[args.model] * 1e9 * B / cfg.n_layer * (16.0 / 16.0)
+    mufu_ops = SCAN_GEXP_PER_WINDOW[args.model] * 1e9 * B / cfg.n_layer * (18.0 / 16.0)
     mufu_rate = mufu_ops / (scan_launch_ms * 1e-3)
     gemm_ms = stage_ms["in_proj"] + stage_ms["out_proj"] + stage_ms["x_proj"] + stage_ms["dt_proj"]
     gemm_tflops = GEMM_GFLOP_PER_WINDOW[args.model] * 1e9 * B / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
@@ -315,7 +315,7 @@ def run_ours(args):
         "roofline_mufu": {
             "kernel": "biscan_kernel", "bound": "mufu (ex2/lg2/rcp special-function pipe: what binds the scan at d_state 16)",
             "achieved": mufu_rate / 1e12, "peak": mufu_peak / 1e12, "unit": "Tops/s", "frac": mufu_rate / mufu_peak,
-            "note": "16 executed MUFU ops per 16 state updates (2 of the 16 exponentials and softplus' log2 run as FMA-pipe polynomials); peak = 16 lanes/clk/SM x 148 SMs x sampled SM clock"},
+            "note": "18 executed MUFU ops per 16 state updates (16 decays + softplus ex2 + gate; softplus' log2 is an FMA-pipe polynomial); peak = 16 lanes/clk/SM x 148 SMs x sampled SM clock"},
         "gemm": {"achieved_tflops": gemm_tflops, "peak_tflops": peaks["bf16"],
                  "frac": (gemm_tflops / peaks["bf16"]) if gemm_tflops else None,
                  "note": "minimal algorithmic FLOPs (in/out_proj once per strand) over the summed GEMM-stage time"},
