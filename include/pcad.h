@@ -153,12 +153,18 @@ int pcad_op_linear_softplus(const void* A, const void* W, const float* bias, voi
  *                             sumsq_out[row][p] = sum over column tile p of (fp32 sum)^2; float [M, pcad_op_sumsq_parts(N)],
  *                             every slot is written with a plain store (no atomics: results are deterministic)
  *   pcad_op_linear_rowscale:  C = (A W^T) * rsqrt(sum_p sumsq_in[row][p] / K + eps)   -- RMSNorm of A's rows applied
- *                             after the GEMM; the norm weight must be pre-multiplied into W's columns by the caller. */
+ *                             after the GEMM; the norm weight must be pre-multiplied into W's columns by the caller.
+ *   pcad_op_linear_rowscale_silu: the same, and columns >= silu_from (a multiple of 64) are stored as SiLU(C): in_proj
+ *                             with the selective scan's gate [selective_scan_fn(..., z): out = y * silu(z)] evaluated in
+ *                             the GEMM epilogue.  Feeds pcad_op_biscan with bit 1 of delta_final set. */
 int pcad_op_sumsq_parts(int N);
 int pcad_op_linear_residual(const void* A, const void* W, const void* resid_in, void* resid_out, float* sumsq_out,
                             int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ld_res, int dtype, void* stream);
 int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in, int sumsq_parts, float eps, void* C,
                             int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream);
+int pcad_op_linear_rowscale_silu(const void* A, const void* W, const float* sumsq_in, int sumsq_parts, float eps,
+                                 int silu_from, void* C, int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc,
+                                 int dtype, void* stream);
 
 /* Fused residual add + RMSNorm [mamba_ssm rms_norm_fn, prenorm=True]:
  * res_out = x + res_in (res_in may be NULL); y = res_out * rsqrt(mean(res_out^2) + eps) * w.
@@ -191,7 +197,9 @@ int pcad_op_conv_xproj(const void* x, int64_t ldx, const float* w_f, const float
  *   D_*, dt_bias_*: float [E];  y: [S*L, E].
  *   delta_final = 0: delta_* are raw dt_proj outputs, the kernel applies softplus(delta + dt_bias) itself (the
  *   reference's order of operations);  delta_final = 1: delta_* already hold softplus(dt_proj + dt_bias)
- *   (pcad_op_linear_softplus) and dt_bias_* are ignored. */
+ *   (pcad_op_linear_softplus) and dt_bias_* are ignored.
+ *   delta_final is a bit set: bit 0 as above; bit 1 (bf16 only): z already holds SiLU(z)
+ *   (pcad_op_linear_rowscale_silu), the kernel multiplies by it as is. */
 int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f,
                    const void* u_r, const void* delta_r, const void* bc_r,
                    int64_t ldbc, int bc_off, const void* z, int64_t ldz,

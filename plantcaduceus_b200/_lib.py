@@ -20,7 +20,7 @@ EXPORTS = (
     "pcad_abi_version", "pcad_create", "pcad_destroy", "pcad_last_error", "pcad_set_weight", "pcad_finalize",
     "pcad_set_tokenizer", "pcad_forward", "pcad_score_masked", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
     "pcad_workspace_bytes", "pcad_set_profiling", "pcad_get_profile", "pcad_launch_count",
-    "pcad_op_linear", "pcad_op_linear_softplus", "pcad_op_linear_residual", "pcad_op_linear_rowscale", "pcad_op_sumsq_parts",
+    "pcad_op_linear", "pcad_op_linear_softplus", "pcad_op_linear_residual", "pcad_op_linear_rowscale", "pcad_op_linear_rowscale_silu", "pcad_op_sumsq_parts",
     "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_conv_xproj", "pcad_op_biscan",
 )
 
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
     lib.pcad_op_linear_softplus.argtypes = [vp, vp, vp, vp, i64, i32, i32, i64, i64, i64, i32, vp]
     lib.pcad_op_linear_residual.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i64, i64, i64, i32, vp]
     lib.pcad_op_linear_rowscale.argtypes = [vp, vp, vp, i32, C.c_float, vp, i64, i32, i32, i64, i64, i64, i32, vp]
+    lib.pcad_op_linear_rowscale_silu.argtypes = [vp, vp, vp, i32, C.c_float, i32, vp, i64, i32, i32, i64, i64, i64, i32, vp]
     lib.pcad_op_sumsq_parts.argtypes = [i32]
     lib.pcad_op_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, i32, i32, vp]
     lib.pcad_op_conv_silu.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]

@@ -58,6 +58,9 @@ struct GemmCfg {
 //                            forward is deterministic and the two strands stay bit-identical;
 //   in_proj,  kEpiRowScale:  C = acc * rsqrt(sum_parts sumsq[row][.] / K + eps), with the norm weight pre-multiplied
 //                            into the columns of W at load time: (r * rstd * w) W^T == rstd * (r (W diag(w))^T).
+//                            Columns >= silu_from (in_proj's z half) are stored as SiLU(C): the selective scan's gate
+//                            [selective_scan_fn(..., z)] computed where the MUFU pipe is idle (this GEMM is bound by
+//                            the tensor pipe, the scan by MUFU); the scan then only multiplies (ZGATED).
 enum { kEpiPlain = 0, kEpiSoftplus = 1, kEpiResidual = 2, kEpiRowScale = 3 };
 
 struct EpiParams {
@@ -69,6 +72,7 @@ struct EpiParams {
   int sumsq_parts = 1;
   float inv_k = 0.f;                  // kEpiRowScale: 1 / (row length the sum of squares was taken over)
   float eps = 0.f;
+  int silu_from = 0x7fffffff;         // kEpiRowScale: columns >= silu_from (a multiple of 64) are stored as SiLU(value)
 };
 
 template <int BN, int EPI, int EW, int CG>
@@ -250,6 +254,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             r0[k] = __float_as_uint(__uint_as_float(r0[k]) * row_scale);
             r1[k] = __float_as_uint(__uint_as_float(r1[k]) * row_scale);
           }
+          if (n0 + c0 >= ep.silu_from) {   // warp-uniform: this 64-column chunk belongs to the gate half
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              r0[k] = __float_as_uint(silu<false>(__uint_as_float(r0[k])));
+              r1[k] = __float_as_uint(silu<false>(__uint_as_float(r1[k])));
+            }
+          }
         }
         if constexpr (EPI == kEpiSoftplus) {
 #pragma unroll
@@ -395,8 +406,8 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
     *why = "gemm: sumsq_parts must equal gemm_sumsq_parts(N)";
     return cudaErrorInvalidValue;
   }
-  if (epi == kEpiRowScale && !ep.sumsq_in) {
-    *why = "gemm: the row-scale epilogue needs sumsq_in";
+  if (epi == kEpiRowScale && (!ep.sumsq_in || (ep.silu_from != 0x7fffffff && (ep.silu_from % 64) != 0))) {
+    *why = "gemm: the row-scale epilogue needs sumsq_in (and silu_from a multiple of 64)";
     return cudaErrorInvalidValue;
   }
   const int BN = pick_bn(N);

@@ -71,6 +71,7 @@ struct pcad_handle {
   int num_sms = 148;
   int d = 0, E = 0, N = 16, R = 0, RP = 0, V = 8;
   bool f32 = false;
+  bool gate_in_gemm = false;           // bf16 + fused norm: SiLU(z) in in_proj's epilogue, the scan only multiplies (ZGATED)
   bool dt_softplus_epilogue = false;   // bf16: softplus(dt_proj + bias) in the GEMM epilogue, scan takes delta as is
   bool fuse_conv_xproj = false;   // bf16: conv + SiLU + both x_proj GEMMs in one kernel (L % 128 == 0)
   bool fuse_norm = false;   // bf16 activations + bf16 residual: add+RMSNorm folded into the out_proj / in_proj epilogues
@@ -316,7 +317,7 @@ int op_conv_xproj(pcad_handle* h, const void* x, long long ldx, const float* w_f
 int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* bc_f, const void* u_r,
               const void* delta_r, const void* bc_r, long long ldbc, int bc_off, const void* z, long long ldz,
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
-              const float* bias_r, void* y, int S, int L, int E, bool f32, bool delta_final, cudaStream_t st) {
+              const float* bias_r, void* y, int S, int L, int E, bool f32, bool delta_final, bool z_gated, cudaStream_t st) {
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
     return fail(h, PCAD_ERR_INVALID, "biscan: E, ldbc, bc_off, ldz must be multiples of %d elements", vec);
@@ -327,7 +328,9 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
   static_cast<const TT*>(u_f), static_cast<const TT*>(delta_f), static_cast<const TT*>(bc_f), static_cast<const TT*>(u_r), \
       static_cast<const TT*>(delta_r), static_cast<const TT*>(bc_r), ldbc, bc_off, static_cast<const TT*>(z), ldz, A_f, D_f, \
       bias_f, A_r, D_r, bias_r, static_cast<TT*>(y), S, L, E, st
+  if (f32 && z_gated) return fail(h, PCAD_ERR_INVALID, "biscan: a pre-gated z is a bf16-path feature");
   if (f32) e = delta_final ? launch_biscan<float, true, true>(PCAD_SCAN_ARGS(float)) : launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float));
+  else if (z_gated) e = delta_final ? launch_biscan<bf16, false, true, true>(PCAD_SCAN_ARGS(bf16)) : launch_biscan<bf16, false, false, true>(PCAD_SCAN_ARGS(bf16));
   else e = delta_final ? launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16)) : launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16));
 #undef PCAD_SCAN_ARGS
   CUDA_TRY(h, e);
@@ -424,6 +427,7 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
         ep.sumsq_parts = parts;
         ep.inv_k = 1.0f / static_cast<float>(d);
         ep.eps = h->cfg.norm_eps;
+        if (h->gate_in_gemm) ep.silu_from = E;   // the z half leaves the GEMM as SiLU(z)
         rc = op_linear(h, ws.resid, lw.in_proj_s, ws.xz, T, 2 * E, d, d, d, 2 * E, false, h->num_sms, st, kEpiRowScale, ep);
       } else {
         rc = op_linear(h, ws.normed, lw.in_proj, ws.xz, T, 2 * E, d, d, d, 2 * E, f32, h->num_sms, st);
@@ -467,7 +471,7 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
       const uint8_t* zbase = static_cast<const uint8_t*>(ws.xz) + static_cast<size_t>(E) * h->act_size;
       rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
                      lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
-                     /*delta_final=*/h->dt_softplus_epilogue, st);
+                     /*delta_final=*/h->dt_softplus_epilogue, /*z_gated=*/fused && h->gate_in_gemm, st);
       if (rc) return rc;
     }
     {
@@ -576,6 +580,11 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   // Off by default: measured zero-sum on B200 (l32, B = 256: scan -11.5 ms, dt_proj +12.3 ms per step), so the
   // forward keeps the reference's order of operations; PCAD_DT_SOFTPLUS_EPILOGUE=1 switches it on for experiments.
   h->dt_softplus_epilogue = false;
+  // SiLU(z) in in_proj's epilogue + a multiply-only scan epilogue.  Off by default: measured zero-sum on B200 (l32,
+  // B = 256: scan -3.4 ms, in_proj +2.9 ms per step -- the forward runs under the power cap, so moving MUFU work
+  // between kernels does not shorten it), and the default keeps the reference's order of operations.
+  h->gate_in_gemm = false;
+  if (const char* gg = getenv("PCAD_GATE_IN_GEMM")) h->gate_in_gemm = h->fuse_norm && (h->E % 64) == 0 && gg[0] == '1';
   if (const char* ds = getenv("PCAD_DT_SOFTPLUS_EPILOGUE")) h->dt_softplus_epilogue = !h->f32 && ds[0] == '1';
   if (const char* nf = getenv("PCAD_NO_FUSED_NORM")) { if (nf[0] == '1') h->fuse_norm = false; }   // A/B switch for tests
   memset(h->prof_ms, 0, sizeof(h->prof_ms));
@@ -995,6 +1004,18 @@ int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in,
   return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiRowScale, ep));
 }
 
+int pcad_op_linear_rowscale_silu(const void* A, const void* W, const float* sumsq_in, int sumsq_parts, float eps, int silu_from, void* C,
+                                 int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 || !sumsq_in || sumsq_parts < 1 || silu_from < 0) return PCAD_ERR_INVALID;
+  EpiParams ep;
+  ep.sumsq_in = sumsq_in;
+  ep.sumsq_parts = sumsq_parts;
+  ep.inv_k = 1.0f / static_cast<float>(K);
+  ep.eps = eps;
+  ep.silu_from = silu_from;
+  return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiRowScale, ep));
+}
+
 int pcad_op_add_rmsnorm(const void* x, const void* res_in, const float* w, void* y, void* res_out, int64_t rows, int d, float eps, int dtype, int res_dtype, void* stream) {
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   if (dtype == PCAD_F32 && res_dtype != PCAD_F32) return PCAD_ERR_INVALID;
@@ -1019,7 +1040,8 @@ int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f, const
                    const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E, int delta_final, int dtype, void* stream) {
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_biscan(op_scratch(), u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
-                                     A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, delta_final != 0, static_cast<cudaStream_t>(stream)));
+                                     A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, (delta_final & 1) != 0, (delta_final & 2) != 0,
+                                     static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

@@ -200,6 +200,7 @@ template <> struct ScanDir<false> {
 };
 
 // DFINAL: delta_* already hold softplus(dt_proj + bias) (the GEMM's softplus epilogue); bias_* are ignored.
+// ZGATED: z already holds SiLU(z) (in_proj's row-scale epilogue with silu_from): the epilogue only multiplies.
 //
 // Staging.  u, delta and B|C of both directions arrive by TMA: six 3-D tensor maps [sequence][row][channel] with a
 // [1][16][128] (B|C: [1][16][32]) box, issued by one thread per chunk into a 2-stage ring and completed on an
@@ -207,7 +208,7 @@ template <> struct ScanDir<false> {
 // either direction) are zero-filled by the hardware.  The reverse direction's box holds ascending rows
 // L-16(c+1) .. L-16c-1, i.e. step j of the chunk sits in box row 15-j.  The parked partials and z rows that the
 // chunk epilogue needs are fetched with cp.async (generic proxy: they were written by this CTA's own st.global).
-template <typename T, bool PRECISE, bool DFINAL>
+template <typename T, bool PRECISE, bool DFINAL, bool ZGATED>
 __global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : PCAD_SCAN_MINBLOCKS)
 biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__ CUtensorMap tm_df,
               const __grid_constant__ CUtensorMap tm_bcf, const __grid_constant__ CUtensorMap tm_ur,
@@ -402,10 +403,13 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
               for (int q = 0; q < 4; ++q) {
                 const f32x2 p2 = pack2(__uint_as_float(pw[q] << 16), __uint_as_float(pw[q] & 0xffff0000u));
                 const f32x2 z2 = pack2(__uint_as_float(zw[q] << 16), __uint_as_float(zw[q] & 0xffff0000u));
-                float x0, x1, d0, d1;
-                unpack2(mul2(z2, nl2), x0, x1);
-                unpack2(add2(pack2(ex2_approx(x0), ex2_approx(x1)), one2), d0, d1);
-                const f32x2 g2 = mul2(z2, pack2(rcp_approx(d0), rcp_approx(d1)));   // SiLU(z)
+                f32x2 g2 = z2;   // ZGATED: already SiLU(z)
+                if constexpr (!ZGATED) {
+                  float x0, x1, d0, d1;
+                  unpack2(mul2(z2, nl2), x0, x1);
+                  unpack2(add2(pack2(ex2_approx(x0), ex2_approx(x1)), one2), d0, d1);
+                  g2 = mul2(z2, pack2(rcp_approx(d0), rcp_approx(d1)));   // SiLU(z)
+                }
                 v2[q] = mul2(add2(v2[q], p2), g2);
               }
             }
@@ -451,7 +455,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
       float zz[VEC];
       load16<T>(&sm.pz[1][dd][j][seg * VEC], zz);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) v[k] *= silu<PRECISE>(zz[k]);
+      for (int k = 0; k < VEC; ++k) v[k] *= ZGATED ? zz[k] : silu<PRECISE>(zz[k]);
       store16<T>(yp, v);
     }
     // no barrier here: the next iteration's first __syncthreads orders these reads of sm.ys and of the stage
@@ -459,7 +463,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   }
 }
 
-template <typename T, bool PRECISE, bool DFINAL>
+template <typename T, bool PRECISE, bool DFINAL, bool ZGATED = false>
 inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, const T* u_r, const T* delta_r,
                                  const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
@@ -468,7 +472,7 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
   size_t smem = sizeof(ScanShared<T>) + 128;   // + alignment slack for the TMA destinations
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static unsigned long long attr_done = 0;
-  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, DFINAL>, static_cast<int>(smem), attr_done);
+  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, DFINAL, ZGATED>, static_cast<int>(smem), attr_done);
   if (e1 != cudaSuccess) return e1;
   constexpr bool f32 = sizeof(T) == 4;
   CUtensorMap tm[6];
@@ -479,7 +483,7 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
   ok = ok && make_tmap_3d(&tm[5], f32, bc_r + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
   if (!ok) return cudaErrorInvalidValue;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
-  biscan_kernel<T, PRECISE, DFINAL><<<grid, kScanThreads, smem, stream>>>(tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], z, ldz, A_f,
+  biscan_kernel<T, PRECISE, DFINAL, ZGATED><<<grid, kScanThreads, smem, stream>>>(tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], z, ldz, A_f,
                                                                 D_f, bias_f, A_r, D_r, bias_r, y, L, E);
   return cudaGetLastError();
 }

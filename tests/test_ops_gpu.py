@@ -100,6 +100,21 @@ def test_linear_residual_and_rowscale_epilogues(lib, cuda_device, M, N, K):
     err = (out.float() - ref).abs().max().item()
     assert not torch.isnan(out.float()).any()
     assert err <= 2 ** -6 * ref.abs().max().item() + 2e-3, err
+    # the same with the gate half (columns >= d) leaving the GEMM as SiLU(value): in_proj + the scan's z gate
+    if d % 64 == 0:
+        out2 = torch.full((M, 2 * d), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+        check(lib, lib.pcad_op_linear_rowscale_silu(ptr(X), ptr(W2s), ptr(sumsq), parts, C.c_float(eps), d, ptr(out2), M, 2 * d, d, d, d, 2 * d, BF16, stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(out2[:, :d], out[:, :d])                      # the x half is untouched, bit for bit
+        ref2 = F.silu(ref[:, d:])
+        assert not torch.isnan(out2.float()).any()
+        assert (out2[:, d:].float() - ref2).abs().max().item() <= 2 ** -6 * ref.abs().max().item() + 2e-3
+        # and it is SiLU of the un-rounded accumulator: within one bf16 ulp of SiLU(rounded plain output) plus the
+        # propagated rounding of its argument
+        plain = F.silu(out[:, d:].float())
+        assert (out2[:, d:].float() - plain).abs().max().item() <= 2 ** -7 * plain.abs().max().item() + 1e-3
+    else:
+        assert lib.pcad_op_linear_rowscale_silu(ptr(X), ptr(W2s), ptr(sumsq), parts, C.c_float(eps), d, ptr(out), M, 2 * d, d, d, d, 2 * d, BF16, stream()) != 0
 
 
 def test_linear_bf16_strided(lib, cuda_device):
@@ -216,7 +231,7 @@ def test_conv_xproj_fused(lib, cuda_device, S, L, E, R):
                                   ptr(wx[0]), ptr(wx[1]), ptr(df), ptr(dr), S, L - 1, E, RP, BF16, stream()) != 0
 
 
-@pytest.mark.parametrize("dtype,delta_final", [(F32, 0), (BF16, 0), (BF16, 1), (F32, 1)])
+@pytest.mark.parametrize("dtype,delta_final", [(F32, 0), (BF16, 0), (BF16, 1), (F32, 1), (BF16, 2), (BF16, 3)])
 @pytest.mark.parametrize("S,L,E,R", [(2, 512, 256, 24), (3, 64, 128, 8), (2, 37, 128, 8), (1, 1, 128, 8), (2, 16, 128, 64), (1, 33, 384, 24),
                                      (1, 40, 128, 8), (1, 47, 200, 8)])
 def test_biscan(lib, cuda_device, dtype, delta_final, S, L, E, R):
@@ -234,6 +249,10 @@ def test_biscan(lib, cuda_device, dtype, delta_final, S, L, E, R):
     bias = [mk(E) - 3 for _ in range(2)]
     bias[0][0] = 30.0   # exercises the softplus threshold branch
     dev = lambda t: t.to(cuda_device).contiguous()
+    z_gated = bool(delta_final & 2)   # bit 1: z already holds SiLU(z) (in_proj's epilogue), rounded to the activation dtype
+    delta_flags, delta_final = delta_final, delta_final & 1
+    if z_gated:
+        xz[:, E:] = F.silu(xz[:, E:].float()).to(td)
     if delta_final:   # the kernel receives softplus(delta + bias), rounded to the activation dtype, and ignores bias
         dl_in = [F.softplus(dl[k].float() + bias[k][None, :]).to(td) for k in range(2)]
     else:
@@ -245,7 +264,7 @@ def test_biscan(lib, cuda_device, dtype, delta_final, S, L, E, R):
     z_ptr = C.c_void_p(xz_d.data_ptr() + E * xz_d.element_size())
     check(lib, lib.pcad_op_biscan(ptr(u_d[0]), ptr(dl_d[0]), ptr(bc_d[0]), ptr(u_d[1]), ptr(dl_d[1]), ptr(bc_d[1]),
                                   RP, R, z_ptr, 2 * E, ptr(A_d[0]), ptr(D_d[0]), ptr(b_d[0]),
-                                  ptr(A_d[1]), ptr(D_d[1]), ptr(b_d[1]), ptr(y), S, L, E, delta_final, dtype, stream()))
+                                  ptr(A_d[1]), ptr(D_d[1]), ptr(b_d[1]), ptr(y), S, L, E, delta_flags, dtype, stream()))
     torch.cuda.synchronize()
 
     # oracle: two selective_scan_ref calls (fp32 maths on the same rounded inputs), reverse one flipped
@@ -267,7 +286,7 @@ def test_biscan(lib, cuda_device, dtype, delta_final, S, L, E, R):
         yy = O.selective_scan_ref(uu, dd, A[k], Bm, Cm, D[k], torch.full_like(uu, 1.0), bias[k]) / F.silu(torch.tensor(1.0))
         ys.append(yy.flip(-1) if k == 1 else yy)
     z = to_bel(xz[:, E:], E)
-    want = ((ys[0] + ys[1]) * F.silu(z)).transpose(1, 2).reshape(S * L, E)
+    want = ((ys[0] + ys[1]) * (z if z_gated else F.silu(z))).transpose(1, 2).reshape(S * L, E)
     got = y.cpu().float()
     assert not torch.isnan(got).any()
     scale = want.abs().max().item()
