@@ -21,7 +21,7 @@ EXPORTS = (
     "pcad_set_tokenizer", "pcad_forward", "pcad_score_masked", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
     "pcad_workspace_bytes", "pcad_set_profiling", "pcad_get_profile", "pcad_launch_count",
     "pcad_op_linear", "pcad_op_linear_softplus", "pcad_op_linear_residual", "pcad_op_linear_rowscale", "pcad_op_linear_rowscale_silu", "pcad_op_sumsq_parts",
-    "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_conv_xproj", "pcad_op_biscan",
+    "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_conv_xproj", "pcad_op_biscan", "pcad_op_biscan_dt", "pcad_op_prep_dt_weight",
 )
 
 
@@ -81,6 +81,8 @@ def load() -> C.CDLL:
     lib.pcad_op_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, i32, i32, vp]
     lib.pcad_op_conv_silu.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.pcad_op_conv_xproj.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.pcad_op_prep_dt_weight.argtypes = [vp, i64, vp, i32, i32, vp]
+    lib.pcad_op_biscan_dt.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.pcad_op_biscan.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp,
                                    i32, i32, i32, i32, i32, vp]
     for name in EXPORTS:

@@ -445,9 +445,10 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 
 // 3D row-major [n2][n1][n0] tensor of bf16 or fp32 (n0 contiguous, row pitch ld elements, n2 slices of n1 rows back to
-// back), box = [1][box1][box0], no swizzle, out-of-range elements read as zero.
+// back), box = [1][box1][box0], no swizzle (or the 128-byte swizzle: box0 * element size must be 128), out-of-range
+// elements read as zero.
 inline bool make_tmap_3d(CUtensorMap* map, bool f32, const void* base, long long n0, long long n1, long long n2,
-                         long long ld, int box0, int box1) {
+                         long long ld, int box0, int box1, bool swizzle128 = false) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   const cuuint64_t es = f32 ? 4 : 2;
@@ -457,7 +458,8 @@ inline bool make_tmap_3d(CUtensorMap* map, bool f32, const void* base, long long
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                    const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 

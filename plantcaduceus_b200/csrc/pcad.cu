@@ -29,6 +29,7 @@ struct DirWeights {
   float* conv_b = nullptr;   // [E]
   void* x_proj = nullptr;    // [RP, E] act dtype, rows >= R+2N zero
   void* dt_proj = nullptr;   // [E, R] act dtype
+  void* dt_proj_p = nullptr; // [E, 64] bf16 in mma B-fragment order (prep_dt_weight_kernel): dt_proj fused into the scan
   float* dt_bias = nullptr;  // [E]
   float* A = nullptr;        // [E, N] = -exp(A_log)
   float* D = nullptr;        // [E]
@@ -71,6 +72,7 @@ struct pcad_handle {
   int num_sms = 148;
   int d = 0, E = 0, N = 16, R = 0, RP = 0, V = 8;
   bool f32 = false;
+  bool fuse_dt = false;                // bf16: dt_proj computed inside the scan (mma.sync), no dt_proj launches, no delta in HBM
   bool gate_in_gemm = false;           // bf16 + fused norm: SiLU(z) in in_proj's epilogue, the scan only multiplies (ZGATED)
   bool dt_softplus_epilogue = false;   // bf16: softplus(dt_proj + bias) in the GEMM epilogue, scan takes delta as is
   bool fuse_conv_xproj = false;   // bf16: conv + SiLU + both x_proj GEMMs in one kernel (L % 128 == 0)
@@ -317,7 +319,8 @@ int op_conv_xproj(pcad_handle* h, const void* x, long long ldx, const float* w_f
 int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* bc_f, const void* u_r,
               const void* delta_r, const void* bc_r, long long ldbc, int bc_off, const void* z, long long ldz,
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
-              const float* bias_r, void* y, int S, int L, int E, bool f32, bool delta_final, bool z_gated, cudaStream_t st) {
+              const float* bias_r, void* y, int S, int L, int E, bool f32, bool delta_final, bool z_gated, cudaStream_t st,
+              const void* wdt_f = nullptr, const void* wdt_r = nullptr) {
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
     return fail(h, PCAD_ERR_INVALID, "biscan: E, ldbc, bc_off, ldz must be multiples of %d elements", vec);
@@ -329,6 +332,22 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
       static_cast<const TT*>(delta_r), static_cast<const TT*>(bc_r), ldbc, bc_off, static_cast<const TT*>(z), ldz, A_f, D_f, \
       bias_f, A_r, D_r, bias_r, static_cast<TT*>(y), S, L, E, st
   if (f32 && z_gated) return fail(h, PCAD_ERR_INVALID, "biscan: a pre-gated z is a bf16-path feature");
+  const bool fused_dt = wdt_f != nullptr || wdt_r != nullptr;
+  if (fused_dt) {   // delta_* are the x_proj outputs, dt_proj runs inside the kernel
+    if (f32 || delta_final || !wdt_f || !wdt_r || ldbc < kScanDtK)
+      return fail(h, PCAD_ERR_INVALID, "biscan: the in-kernel dt_proj needs bf16, raw delta, both weights and ldbc >= 64");
+    cudaError_t e2;
+#define PCAD_SCAN_ARGS_DT                                                                                               \
+  static_cast<const bf16*>(u_f), static_cast<const bf16*>(delta_f), static_cast<const bf16*>(bc_f),                       \
+      static_cast<const bf16*>(u_r), static_cast<const bf16*>(delta_r), static_cast<const bf16*>(bc_r), ldbc, bc_off,       \
+      static_cast<const bf16*>(z), ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, static_cast<bf16*>(y), S, L, E, st,             \
+      static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r)
+    if (z_gated) e2 = launch_biscan<bf16, false, false, true, true>(PCAD_SCAN_ARGS_DT);
+    else e2 = launch_biscan<bf16, false, false, false, true>(PCAD_SCAN_ARGS_DT);
+#undef PCAD_SCAN_ARGS_DT
+    CUDA_TRY(h, e2);
+    return PCAD_OK;
+  }
   if (f32) e = delta_final ? launch_biscan<float, true, true>(PCAD_SCAN_ARGS(float)) : launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float));
   else if (z_gated) e = delta_final ? launch_biscan<bf16, false, true, true>(PCAD_SCAN_ARGS(bf16)) : launch_biscan<bf16, false, false, true>(PCAD_SCAN_ARGS(bf16));
   else e = delta_final ? launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16)) : launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16));
@@ -452,7 +471,7 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
         rc = op_linear(h, ws.xc[dir], lw.dir[dir].x_proj, ws.dbc[dir], T, RP, E, E, E, RP, f32, h->num_sms, st);
         if (rc) return rc;
       }
-      {
+      if (!h->fuse_dt) {
         StageTimer tm(h, st, PCAD_ST_DT_PROJ);
         // Optional (bf16): softplus(dt_proj + bias) in the GEMM epilogue (8 epilogue warps) so the MUFU-bound scan gets
         // delta ready-made (delta_final).  Default and fp32: the reference's order (raw dt_proj, softplus in the scan).
@@ -469,9 +488,14 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
     {
       StageTimer tm(h, st, PCAD_ST_SCAN);
       const uint8_t* zbase = static_cast<const uint8_t*>(ws.xz) + static_cast<size_t>(E) * h->act_size;
-      rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
-                     lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
-                     /*delta_final=*/h->dt_softplus_epilogue, /*z_gated=*/fused && h->gate_in_gemm, st);
+      if (h->fuse_dt)   // dt_proj inside the scan: it reads the x_proj outputs (dt | B | C) and the re-laid dt_proj weights
+        rc = op_biscan(h, ws.xc[0], ws.dbc[0], ws.dbc[0], ws.xc[1], ws.dbc[1], ws.dbc[1], RP, R, zbase, 2 * E,
+                       lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
+                       false, /*z_gated=*/fused && h->gate_in_gemm, st, lw.dir[0].dt_proj_p, lw.dir[1].dt_proj_p);
+      else
+        rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
+                       lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
+                       /*delta_final=*/h->dt_softplus_epilogue, /*z_gated=*/fused && h->gate_in_gemm, st);
       if (rc) return rc;
     }
     {
@@ -580,12 +604,17 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   // Off by default: measured zero-sum on B200 (l32, B = 256: scan -11.5 ms, dt_proj +12.3 ms per step), so the
   // forward keeps the reference's order of operations; PCAD_DT_SOFTPLUS_EPILOGUE=1 switches it on for experiments.
   h->dt_softplus_epilogue = false;
+  if (const char* ds = getenv("PCAD_DT_SOFTPLUS_EPILOGUE")) h->dt_softplus_epilogue = !h->f32 && ds[0] == '1';
+  // dt_proj inside the scan kernel (bf16; x_proj output rows must hold at least 64 columns for the TMA box).
+  // Off by default: measured slower on B200 (scan +30 ms, dt_proj -12.5 ms per step; see scan.cuh).
+  h->fuse_dt = false;
+  if (const char* fd = getenv("PCAD_FUSED_DT"))
+    h->fuse_dt = fd[0] == '1' && !h->f32 && !h->dt_softplus_epilogue && h->RP >= kScanDtK && h->R <= kScanDtK && (h->E % 8) == 0;
   // SiLU(z) in in_proj's epilogue + a multiply-only scan epilogue.  Off by default: measured zero-sum on B200 (l32,
   // B = 256: scan -3.4 ms, in_proj +2.9 ms per step -- the forward runs under the power cap, so moving MUFU work
   // between kernels does not shorten it), and the default keeps the reference's order of operations.
   h->gate_in_gemm = false;
   if (const char* gg = getenv("PCAD_GATE_IN_GEMM")) h->gate_in_gemm = h->fuse_norm && (h->E % 64) == 0 && gg[0] == '1';
-  if (const char* ds = getenv("PCAD_DT_SOFTPLUS_EPILOGUE")) h->dt_softplus_epilogue = !h->f32 && ds[0] == '1';
   if (const char* nf = getenv("PCAD_NO_FUSED_NORM")) { if (nf[0] == '1') h->fuse_norm = false; }   // A/B switch for tests
   memset(h->prof_ms, 0, sizeof(h->prof_ms));
   memset(h->prof_launches, 0, sizeof(h->prof_launches));
@@ -611,6 +640,7 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
       rc |= dev_alloc(h, &dw.conv_b, h->E);
       rc |= A8(&dw.x_proj, static_cast<size_t>(h->RP) * h->E * a);
       rc |= A8(&dw.dt_proj, static_cast<size_t>(h->E) * h->R * a);
+      if (!h->f32) rc |= A8(&dw.dt_proj_p, static_cast<size_t>(h->E) * kScanDtK * 2);
       rc |= dev_alloc(h, &dw.dt_bias, h->E);
       rc |= dev_alloc(h, &dw.A, static_cast<size_t>(h->E) * h->N);
       rc |= dev_alloc(h, &dw.D, h->E);
@@ -787,6 +817,16 @@ int pcad_finalize(pcad_handle* h) {
     for (auto& lw : h->layers)
       scale_columns_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(static_cast<const bf16*>(lw.in_proj), lw.norm_w,
                                                                            static_cast<bf16*>(lw.in_proj_s), rows, h->d);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+  }
+  if (h->fuse_dt) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long n = static_cast<long long>(h->E) * kScanDtK;
+    for (auto& lw : h->layers)
+      for (int dir = 0; dir < 2; ++dir)
+        prep_dt_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(static_cast<const bf16*>(lw.dir[dir].dt_proj), h->R,
+                                                                              static_cast<bf16*>(lw.dir[dir].dt_proj_p), h->E, h->R);
+    CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaDeviceSynchronize());
   }
   h->finalized = true;
@@ -1014,6 +1054,24 @@ int pcad_op_linear_rowscale_silu(const void* A, const void* W, const float* sums
   ep.eps = eps;
   ep.silu_from = silu_from;
   return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiRowScale, ep));
+}
+
+int pcad_op_prep_dt_weight(const void* W, int64_t ldw, void* out, int E, int R, void* stream) {
+  if (!W || !out || E <= 0 || R <= 0 || R > kScanDtK || ldw < R) return PCAD_ERR_INVALID;
+  const long long n = static_cast<long long>(E) * kScanDtK;
+  prep_dt_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), E, R);
+  return cudaGetLastError() == cudaSuccess ? PCAD_OK : PCAD_ERR_CUDA;
+}
+
+int pcad_op_biscan_dt(const void* u_f, const void* dbc_f, const void* u_r, const void* dbc_r, int64_t ldbc, int bc_off,
+                      const void* wdt_f, const void* wdt_r, const void* z, int64_t ldz, const float* A_f, const float* D_f,
+                      const float* dt_bias_f, const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E,
+                      int flags, void* stream) {
+  if (!wdt_f || !wdt_r || (flags & 1)) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_biscan(op_scratch(), u_f, dbc_f, dbc_f, u_r, dbc_r, dbc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
+                                     A_r, D_r, dt_bias_r, y, S, L, E, false, false, (flags & 2) != 0, static_cast<cudaStream_t>(stream),
+                                     wdt_f, wdt_r));
 }
 
 int pcad_op_add_rmsnorm(const void* x, const void* res_in, const float* w, void* y, void* res_out, int64_t rows, int d, float eps, int dtype, int res_dtype, void* stream) {

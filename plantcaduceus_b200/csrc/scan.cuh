@@ -68,19 +68,41 @@ constexpr int kScanUnroll = PCAD_SCAN_UNROLL;   // main-loop unroll (2 removes t
 
 template <int V> struct IntTag { static constexpr int value = V; };
 
+constexpr int kScanDtK = 64;        // FUSEDT: contraction length of the in-kernel dt_proj (dt_rank zero-padded to 64)
+constexpr int kScanDlPitch = 136;   // FUSEDT: row pitch (elements) of the delta tile: 272 B = 68 words -> conflict-free fragment stores
+
+// FUSEDT = false: delta arrives ready-made (dt_proj ran as a GEMM).  FUSEDT = true (bf16): the stage carries the
+// rank-R dt rows instead ([16][64] tile, 128-byte swizzled by TMA so that mma A-fragments are read without bank
+// conflicts; it comes first because the swizzle atom needs 1024-byte alignment) and each warp computes its own
+// 16 x 32 delta tile with mma.sync before the main loop.
+template <typename T, bool FUSEDT> struct ScanStage;
 template <typename T>
-struct ScanStage {
+struct ScanStage<T, false> {
   T u[2][kScanTC][kScanCH];          // [direction][step][channel]
   T d[2][kScanTC][kScanCH];
   T bc_raw[2][kScanTC][2 * kScanN];
 };
-
 template <typename T>
+struct ScanStage<T, true> {
+  T dt[2][kScanTC][kScanDtK];        // x_proj output columns 0..63 (dt | whatever follows: the padded weight zeroes it)
+  T u[2][kScanTC][kScanCH];
+  T bc_raw[2][kScanTC][2 * kScanN];
+};
+
+template <typename T, bool FUSEDT>
 struct ScanShared {
-  ScanStage<T> st[2];
+  ScanStage<T, FUSEDT> st[2];
   float bc[2][kScanTC][2 * kScanN];   // fp32 B|C of the chunk being computed
   T pz[2][2][kScanTC][kScanCH];       // [partial | z][direction][step][channel]: prefetched for the chunk epilogue
+  T dl[FUSEDT ? 2 : 1][FUSEDT ? kScanTC : 1][FUSEDT ? kScanDlPitch : 8];   // FUSEDT: delta of the chunk, per direction
 };
+
+// mma.sync m16n8k16, bf16 inputs, fp32 accumulate (row-major A fragment, column-major B fragment)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 // One direction's 16 states of one channel.  step() advances h <- exp(d*A) h + du*B and returns
 // y0 + <C, h>;  bc points at this timestep's fp32 [B(16) | C(16)] row in shared memory (broadcast reads).
@@ -208,18 +230,33 @@ template <> struct ScanDir<false> {
 // either direction) are zero-filled by the hardware.  The reverse direction's box holds ascending rows
 // L-16(c+1) .. L-16c-1, i.e. step j of the chunk sits in box row 15-j.  The parked partials and z rows that the
 // chunk epilogue needs are fetched with cp.async (generic proxy: they were written by this CTA's own st.global).
-template <typename T, bool PRECISE, bool DFINAL, bool ZGATED>
+//
+// FUSEDT (bf16): tm_df / tm_dr map the x_proj outputs (columns 0..63, 128-byte swizzle) instead of delta, and
+// wdt_f / wdt_r are dt_proj.weight re-laid for the mma B-fragments (prep_dt_weight_kernel): dt_proj
+// [EXT Mamba.dt_proj, F.linear(dt, W)] runs inside the scan, one 16 x 32 x 64 product per warp and chunk, its fp32
+// accumulators rounded to bf16 exactly where the GEMM would have rounded them -- the two dt_proj launches of a layer
+// and the 4 KB per token of delta they write and the scan re-reads disappear.  Measured on B200 (l32, B = 256): the
+// dt_proj stage goes away (-12.5 ms per step) and the SM clock rises (less HBM traffic under the power cap), but the scan
+// grows by 30 ms: at 3 CTAs/SM there are neither the 32 registers to keep the weight fragments nor the 32 KB of shared
+// memory to stage them, so every chunk re-reads them from L2 and the warp waits out that latency with the MUFU pipe idle
+// (block order does not change it).  Opt-in (PCAD_FUSED_DT=1); it belongs with a 2-CTA/SM layout.
+template <typename T, bool PRECISE, bool DFINAL, bool ZGATED, bool FUSEDT>
 __global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : PCAD_SCAN_MINBLOCKS)
 biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__ CUtensorMap tm_df,
               const __grid_constant__ CUtensorMap tm_bcf, const __grid_constant__ CUtensorMap tm_ur,
               const __grid_constant__ CUtensorMap tm_dr, const __grid_constant__ CUtensorMap tm_bcr,
+              const T* __restrict__ wdt_f, const T* __restrict__ wdt_r,
               const T* __restrict__ z, long long ldz, const float* __restrict__ A_f, const float* __restrict__ D_f,
               const float* __restrict__ bias_f, const float* __restrict__ A_r, const float* __restrict__ D_r,
               const float* __restrict__ bias_r, T* y, int L, int E) {
+  static_assert(!FUSEDT || (sizeof(T) == 2 && !PRECISE && !DFINAL), "the in-kernel dt_proj is a bf16-path feature");
   extern __shared__ __align__(128) uint8_t scan_smem_raw[];
-  // TMA destinations must be 128-byte aligned; the runtime only promises 16 for the dynamic segment
-  // (pointer arithmetic on the array itself, so that the accesses stay in the shared address space)
-  ScanShared<T>& sm = *reinterpret_cast<ScanShared<T>*>(scan_smem_raw + ((128u - (smem_u32(scan_smem_raw) & 127u)) & 127u));
+  // TMA destinations must be 128-byte aligned (1024 for the swizzled dt tiles); the runtime only promises 16 for the
+  // dynamic segment (pointer arithmetic on the array itself, so that the accesses stay in the shared address space)
+  constexpr uint32_t kAlign = FUSEDT ? 1024u : 128u;
+  typedef ScanShared<T, FUSEDT> Shared;
+  typedef ScanStage<T, FUSEDT> Stage;
+  Shared& sm = *reinterpret_cast<Shared*>(scan_smem_raw + ((kAlign - (smem_u32(scan_smem_raw) & (kAlign - 1u))) & (kAlign - 1u)));
   // Un-gated outputs of the chunk, per direction.  A separate (static) symbol on purpose: the compiler can then
   // prove that the main loop's stores to it do not alias the loads of later steps and overlaps consecutive steps.
   __shared__ __align__(16) float ys[2][kScanTC][kScanCH];
@@ -236,7 +273,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   const int nch = (L + kScanTC - 1) / kScanTC;
   constexpr int VEC = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int SEGS = kScanCH / VEC;              // 16-byte segments per 128-channel row
-  constexpr uint32_t kStageBytes = sizeof(ScanStage<T>);
+  constexpr uint32_t kStageBytes = sizeof(Stage);
 
   if (tid == 0) {
     mbar_init(&full_bar[0], 1);
@@ -249,16 +286,21 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
 
   // chunk c: forward rows 16c .. 16c+15, reverse rows L-16(c+1) .. L-16c-1 (box row 15-j = step j).  One thread.
   auto issue = [&](int c, int stage) {
-    ScanStage<T>& s = sm.st[stage];
+    Stage& s = sm.st[stage];
     uint64_t* bar = &full_bar[stage];
     mbar_arrive_expect_tx(bar, kStageBytes);
     const int rf = c * kScanTC, rr = L - (c + 1) * kScanTC;
     tma_load_3d(&s.u[0][0][0], &tm_uf, bar, e0, rf, seq);
-    tma_load_3d(&s.d[0][0][0], &tm_df, bar, e0, rf, seq);
     tma_load_3d(&s.bc_raw[0][0][0], &tm_bcf, bar, 0, rf, seq);
     tma_load_3d(&s.u[1][0][0], &tm_ur, bar, e0, rr, seq);
-    tma_load_3d(&s.d[1][0][0], &tm_dr, bar, e0, rr, seq);
     tma_load_3d(&s.bc_raw[1][0][0], &tm_bcr, bar, 0, rr, seq);
+    if constexpr (FUSEDT) {
+      tma_load_3d(&s.dt[0][0][0], &tm_df, bar, 0, rf, seq);
+      tma_load_3d(&s.dt[1][0][0], &tm_dr, bar, 0, rr, seq);
+    } else {
+      tma_load_3d(&s.d[0][0][0], &tm_df, bar, e0, rf, seq);
+      tma_load_3d(&s.d[1][0][0], &tm_dr, bar, e0, rr, seq);
+    }
   };
 
   ScanDir<PRECISE> S;
@@ -275,11 +317,50 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     const int stage = c & 1;
     // every thread is past the barrier that followed chunk c-1's main loop: stage^1 is free to be overwritten
     if (tid == 0 && c + 1 < nch) issue(c + 1, stage ^ 1);
-    const ScanStage<T>& s = sm.st[stage];
+    const Stage& s = sm.st[stage];
     const int i0 = c * kScanTC;
     const int nsteps = min(kScanTC, L - i0);
     const bool has_final = (L - 1 - (i0 + nsteps - 1)) < i0 + nsteps;
     mbar_wait(&full_bar[stage], (c >> 1) & 1);
+    if constexpr (FUSEDT) {
+      // delta[16 rows][this warp's 32 channels] = dt[16][64] x W_dt[32][64]^T.  A-fragments from the swizzled tile
+      // (16-byte chunk c of row r sits at chunk c ^ (r & 7)); B-fragments straight from global / L2 in the
+      // per-lane order prep_dt_weight_kernel left them in (32 contiguous bytes per channel and lane quarter).
+      const int lane = tid & 31, g = lane >> 2, q = lane & 3;
+      const int wch0 = ((tid >> 5) & 3) * 32;
+      const uint8_t* dtile = reinterpret_cast<const uint8_t*>(&s.dt[dir][0][0]);
+      uint32_t afr[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {          // k half: columns ks*16 + hh*8 + q*2 live in 16-byte chunk ks*2 + hh
+          const int chunk = ks * 2 + hh;
+          afr[ks][hh * 2 + 0] = *reinterpret_cast<const uint32_t*>(dtile + g * 128 + ((chunk ^ g) << 4) + q * 4);
+          afr[ks][hh * 2 + 1] = *reinterpret_cast<const uint32_t*>(dtile + (g + 8) * 128 + ((chunk ^ g) << 4) + q * 4);
+        }
+      }
+      const T* wdt = dir ? wdt_r : wdt_f;
+      T* dlw = &sm.dl[dir][0][0];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int cch = wch0 + nt * 8 + g;        // channel (within the block's 128) whose weights this lane holds
+        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
+        if (e0 + cch < E) {
+          const uint4* wp = reinterpret_cast<const uint4*>(wdt + (static_cast<long long>(e0 + cch) * kScanDtK + q * 16));
+          w0 = __ldg(wp);
+          w1 = __ldg(wp + 1);
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(acc, afr[0], w0.x, w0.y);
+        mma_bf16_16816(acc, afr[1], w0.z, w0.w);
+        mma_bf16_16816(acc, afr[2], w1.x, w1.y);
+        mma_bf16_16816(acc, afr[3], w1.z, w1.w);
+        const int col = wch0 + nt * 8 + q * 2;
+        *reinterpret_cast<uint32_t*>(dlw + g * kScanDlPitch + col) = pack_bf16x2(acc[0], acc[1]);
+        *reinterpret_cast<uint32_t*>(dlw + (g + 8) * kScanDlPitch + col) = pack_bf16x2(acc[2], acc[3]);
+      }
+      __syncwarp();   // the warp consumes exactly the 32 channels it produced
+    }
     // B|C to fp32, once per chunk, 4 values per thread (B carries the ln 2 of the log2-domain delta on the fast
     // path); the reverse direction's rows are un-flipped here so that the main loop indexes both alike
     {
@@ -336,20 +417,23 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
       auto run_chunk = [&](auto rev_tag) {
         constexpr bool REV = decltype(rev_tag)::value != 0;   // compile-time row order: immediate offsets in the unrolled loop
         const T* up = &s.u[REV ? 1 : 0][0][ch];
-        const T* dp = &s.d[REV ? 1 : 0][0][ch];
         auto row = [](int j) { return (REV ? kScanTC - 1 - j : j) * kScanCH; };
+        auto drow = [](int j) { return (REV ? kScanTC - 1 - j : j) * (FUSEDT ? kScanDlPitch : kScanCH); };
+        const T* dp;
+        if constexpr (FUSEDT) dp = &sm.dl[REV ? 1 : 0][0][ch];
+        else dp = &s.d[REV ? 1 : 0][0][ch];
         // softplus runs one step ahead of the recurrence, so its LDS -> EX2 -> polynomial latency chain is off the
         // critical path of the step that consumes it
         float uu = ActT<T>::to_f(up[row(0)]);
         float dl;
         {
-          const float draw = ActT<T>::to_f(dp[row(0)]);
+          const float draw = ActT<T>::to_f(dp[drow(0)]);
           dl = DFINAL ? S.delta_final(draw) : S.delta(draw);
         }
         auto advance = [&](int j) -> float {
           const int jn = min(j + 1, kScanTC - 1);
           const float uu_n = ActT<T>::to_f(up[row(jn)]);
-          const float draw_n = ActT<T>::to_f(dp[row(jn)]);
+          const float draw_n = ActT<T>::to_f(dp[drow(jn)]);
           const float dl_n = DFINAL ? S.delta_final(draw_n) : S.delta(draw_n);
           const float yv = S.template step<kScanPoly>(dl, dl * uu, Dskip * uu, bcp + j * 2 * kScanN);
           uu = uu_n;
@@ -463,28 +547,47 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   }
 }
 
-template <typename T, bool PRECISE, bool DFINAL, bool ZGATED = false>
+// dt_proj.weight [E, R] (row pitch ldw) -> [E, 64] in the order the FUSEDT kernel's mma B-fragments are read: for lane
+// quarter q, k-step ks, half h, element e:  out[c][q*16 + ks*4 + h*2 + e] = W[c][ks*16 + h*8 + q*2 + e]  (0 for k >= R).
+__global__ void prep_dt_weight_kernel(const bf16* __restrict__ W, long long ldw, bf16* __restrict__ out, int E, int R) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(E) * kScanDtK) return;
+  const int c = static_cast<int>(idx / kScanDtK), o = static_cast<int>(idx % kScanDtK);
+  const int q = o >> 4, ks = (o >> 2) & 3, hh = (o >> 1) & 1, e = o & 1;
+  const int k = ks * 16 + hh * 8 + q * 2 + e;
+  out[idx] = k < R ? W[c * ldw + k] : __float2bfloat16(0.f);
+}
+
+// FUSEDT = true: delta_f / delta_r are the x_proj outputs ([S*L, ldbc], dt in columns 0..R-1, ldbc >= 64) and wdt_f / wdt_r
+// the weights from prep_dt_weight_kernel; otherwise delta_* are [S*L, E] and wdt_* unused.
+template <typename T, bool PRECISE, bool DFINAL, bool ZGATED = false, bool FUSEDT = false>
 inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, const T* u_r, const T* delta_r,
                                  const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
                                  const float* D_r, const float* bias_r, T* y, int S, int L, int E,
-                                 cudaStream_t stream) {
-  size_t smem = sizeof(ScanShared<T>) + 128;   // + alignment slack for the TMA destinations
+                                 cudaStream_t stream, const T* wdt_f = nullptr, const T* wdt_r = nullptr) {
+  size_t smem = sizeof(ScanShared<T, FUSEDT>) + (FUSEDT ? 1024 : 128);   // + alignment slack for the TMA destinations
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static unsigned long long attr_done = 0;
-  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, DFINAL, ZGATED>, static_cast<int>(smem), attr_done);
+  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, DFINAL, ZGATED, FUSEDT>, static_cast<int>(smem), attr_done);
   if (e1 != cudaSuccess) return e1;
   constexpr bool f32 = sizeof(T) == 4;
   CUtensorMap tm[6];
-  const T* act[4] = {u_f, delta_f, u_r, delta_r};
-  bool ok = true;
-  for (int i = 0; i < 4 && ok; ++i) ok = make_tmap_3d(&tm[i], f32, act[i], E, L, S, E, kScanCH, kScanTC);
+  bool ok = make_tmap_3d(&tm[0], f32, u_f, E, L, S, E, kScanCH, kScanTC) && make_tmap_3d(&tm[2], f32, u_r, E, L, S, E, kScanCH, kScanTC);
+  if (FUSEDT) {
+    if (ldbc < kScanDtK || !wdt_f || !wdt_r) return cudaErrorInvalidValue;
+    ok = ok && make_tmap_3d(&tm[1], f32, delta_f, ldbc, L, S, ldbc, kScanDtK, kScanTC, true) &&
+         make_tmap_3d(&tm[3], f32, delta_r, ldbc, L, S, ldbc, kScanDtK, kScanTC, true);
+  } else {
+    ok = ok && make_tmap_3d(&tm[1], f32, delta_f, E, L, S, E, kScanCH, kScanTC) &&
+         make_tmap_3d(&tm[3], f32, delta_r, E, L, S, E, kScanCH, kScanTC);
+  }
   ok = ok && make_tmap_3d(&tm[4], f32, bc_f + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
   ok = ok && make_tmap_3d(&tm[5], f32, bc_r + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
   if (!ok) return cudaErrorInvalidValue;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
-  biscan_kernel<T, PRECISE, DFINAL, ZGATED><<<grid, kScanThreads, smem, stream>>>(tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], z, ldz, A_f,
-                                                                D_f, bias_f, A_r, D_r, bias_r, y, L, E);
+  biscan_kernel<T, PRECISE, DFINAL, ZGATED, FUSEDT><<<grid, kScanThreads, smem, stream>>>(
+      tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], wdt_f, wdt_r, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E);
   return cudaGetLastError();
 }
 

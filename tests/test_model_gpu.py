@@ -142,6 +142,25 @@ def test_bf16_fused_norm_matches_unfused(Model, cuda_device, monkeypatch):
     assert (a - b).abs().max().item() <= 2e-2
 
 
+def test_bf16_in_kernel_dt_proj_matches_separate_gemm(Model, cuda_device, monkeypatch):
+    """PCAD_FUSED_DT=1 computes dt_proj inside the scan kernel (opt-in: measured slower at 3 CTAs/SM); the default runs
+    the dt_proj GEMMs and materialises delta.  Same roundings in both, so the logits agree far inside the bf16 parity bar."""
+    cfg = CaduceusConfig(d_model=512, n_layer=3)     # dt_rank 32, x_proj rows of 64 columns: the fused path is eligible
+    sd = random_init_state_dict(cfg, seed=4)
+    ids = make_ids(3, 200, seed=2, mask_at=100)
+    want, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    split = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    b = split(input_ids=ids.to(cuda_device)).logits.cpu()
+    monkeypatch.setenv("PCAD_FUSED_DT", "1")
+    fused = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    a = fused(input_ids=ids.to(cuda_device)).logits.cpu()
+    assert fused.launch_count() < split.launch_count()          # the dt_proj launches are gone
+    ea, eb = (a - want).abs().max().item(), (b - want).abs().max().item()
+    print(f"in-kernel dt_proj {ea:.4g}  separate GEMM {eb:.4g}")
+    assert ea <= max(2e-2, 1.5 * eb)
+    assert (a - b).abs().max().item() <= 1e-2
+
+
 @pytest.mark.parametrize("env", ["PCAD_GATE_IN_GEMM", "PCAD_DT_SOFTPLUS_EPILOGUE"])
 def test_bf16_optional_epilogue_fusions_match_default(Model, cuda_device, monkeypatch, env):
     """The two opt-in fusions that move MUFU work out of the scan (SiLU(z) into in_proj's epilogue, softplus into

@@ -294,3 +294,57 @@ def test_biscan(lib, cuda_device, dtype, delta_final, S, L, E, R):
         assert (got - want).abs().max().item() <= 2e-5 * scale + 1e-5
     else:
         assert (got - want).abs().max().item() <= 2 ** -6 * scale
+
+
+@pytest.mark.parametrize("flags", [0, 2])
+@pytest.mark.parametrize("S,L,E,R", [(2, 512, 256, 24), (3, 64, 128, 32), (2, 37, 128, 48), (1, 1, 128, 64), (1, 33, 384, 24),
+                                     (1, 47, 200, 64), (2, 100, 2048, 64)])
+def test_biscan_with_in_kernel_dt_proj(lib, cuda_device, S, L, E, R, flags):
+    """pcad_op_biscan_dt (dt_proj computed inside the scan with mma.sync from the x_proj outputs) against the two-kernel
+    path it replaces: pcad_op_linear for delta, then pcad_op_biscan.  Both round delta to bf16 from an fp32 accumulator, so
+    they may differ only where the accumulation order moved a value across a rounding boundary."""
+    N = 16
+    g = torch.Generator().manual_seed(S * 100 + L + R)
+    RP = max((R + 2 * N + 15) // 16 * 16, 64)
+    mk = lambda *shape: torch.randn(*shape, generator=g)
+    bf = lambda t: t.to(cuda_device, torch.bfloat16).contiguous()
+    u = [bf(mk(S * L, E)) for _ in range(2)]
+    dbc = [bf(mk(S * L, RP)) for _ in range(2)]            # [dt (R) | B (16) | C (16) | padding]: every column non-zero
+    W = [bf(mk(E, R) * (0.5 / R ** 0.5)) for _ in range(2)]
+    xz = mk(S * L, 2 * E)
+    if flags & 2:
+        xz[:, E:] = F.silu(xz[:, E:])
+    xz = bf(xz)
+    A = [(-(torch.rand(E, N, generator=g) * 4 + 0.1)).to(cuda_device) for _ in range(2)]
+    D = [mk(E).to(cuda_device) for _ in range(2)]
+    bias = [(mk(E) - 3).to(cuda_device) for _ in range(2)]
+    z_ptr = C.c_void_p(xz.data_ptr() + E * 2)
+    # reference path: delta by the GEMM, then the scan
+    delta = [torch.empty(S * L, E, device=cuda_device, dtype=torch.bfloat16) for _ in range(2)]
+    for k in range(2):
+        check(lib, lib.pcad_op_linear(ptr(dbc[k]), ptr(W[k]), ptr(delta[k]), S * L, E, R, RP, R, E, BF16, stream()))
+    y_ref = torch.full((S * L, E), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    check(lib, lib.pcad_op_biscan(ptr(u[0]), ptr(delta[0]), ptr(dbc[0]), ptr(u[1]), ptr(delta[1]), ptr(dbc[1]), RP, R, z_ptr, 2 * E,
+                                  ptr(A[0]), ptr(D[0]), ptr(bias[0]), ptr(A[1]), ptr(D[1]), ptr(bias[1]), ptr(y_ref), S, L, E, flags, BF16, stream()))
+    # fused path
+    Wp = [torch.full((E, 64), float("nan"), device=cuda_device, dtype=torch.bfloat16) for _ in range(2)]
+    for k in range(2):
+        check(lib, lib.pcad_op_prep_dt_weight(ptr(W[k]), R, ptr(Wp[k]), E, R, stream()))
+    y = torch.full((S * L, E), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    check(lib, lib.pcad_op_biscan_dt(ptr(u[0]), ptr(dbc[0]), ptr(u[1]), ptr(dbc[1]), RP, R, ptr(Wp[0]), ptr(Wp[1]), z_ptr, 2 * E,
+                                     ptr(A[0]), ptr(D[0]), ptr(bias[0]), ptr(A[1]), ptr(D[1]), ptr(bias[1]), ptr(y), S, L, E, flags, stream()))
+    torch.cuda.synchronize()
+    for k in range(2):   # the re-laid weights are a permutation of W padded with zeros
+        assert not torch.isnan(Wp[k].float()).any()
+        assert torch.equal(Wp[k].float().abs().sum(), W[k].float().abs().sum()) or \
+            abs(Wp[k].float().abs().sum().item() - W[k].float().abs().sum().item()) <= 1e-3 * W[k].float().abs().sum().item()
+    got, want = y.float(), y_ref.float()
+    assert not torch.isnan(got).any()
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() <= 2 ** -6 * scale + 1e-3
+    assert (got == want).float().mean().item() >= 0.97   # almost everywhere bit-identical
+    # argument checks: raw delta only, both weights, ldbc >= 64
+    assert lib.pcad_op_biscan_dt(ptr(u[0]), ptr(dbc[0]), ptr(u[1]), ptr(dbc[1]), RP, R, ptr(Wp[0]), ptr(Wp[1]), z_ptr, 2 * E,
+                                 ptr(A[0]), ptr(D[0]), ptr(bias[0]), ptr(A[1]), ptr(D[1]), ptr(bias[1]), ptr(y), S, L, E, 1, stream()) != 0
+    assert lib.pcad_op_biscan_dt(ptr(u[0]), ptr(dbc[0]), ptr(u[1]), ptr(dbc[1]), 48, R, ptr(Wp[0]), ptr(Wp[1]), z_ptr, 2 * E,
+                                 ptr(A[0]), ptr(D[0]), ptr(bias[0]), ptr(A[1]), ptr(D[1]), ptr(bias[1]), ptr(y), S, L, E, flags, stream()) != 0
