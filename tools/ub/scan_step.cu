@@ -172,6 +172,84 @@ void runp(const char* name) {
   cudaFree(out); cudaFree(cyc); delete[] h;
 }
 
+// two channels per thread sharing the B|C reads (the 2-CTA/SM layout sketched in DESIGN.md section 4): per step one set
+// of 8 LDS.128 feeds two independent recurrences; 16 states x 2 + 16 A x 2 registers per thread -> 128-register budget
+template <int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k2ch(float* out, long long* cyc, int iters) {
+  __shared__ __align__(16) float bc[16][32];
+  __shared__ __align__(16) float ys[4][WARPS * 64];
+  __shared__ __nv_bfloat16 dsm[16][256], usm[16][256];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 16 * 32; i += blockDim.x) bc[i / 32][i % 32] = 0.01f * ((i * 7) % 13) - 0.05f;
+  for (int j = 0; j < 16; ++j)
+    for (int i = tid; i < 256; i += blockDim.x) {
+      dsm[j][i] = __float2bfloat16(0.1f * ((i + j) % 7) - 0.3f);
+      usm[j][i] = __float2bfloat16(0.2f * ((i * 3 + j) % 5) - 0.4f);
+    }
+  float A[16];
+  ScanDir<false> S0, S1;
+  for (int n = 0; n < 16; ++n) A[n] = -(n + 1.0f) * (1.0f + 1e-4f * (tid % 97)) * kLog2e;
+  S0.init(A, -4.0f);
+  for (int n = 0; n < 16; ++n) A[n] *= 1.01f;
+  S1.init(A, -4.1f);
+  __syncthreads();
+  const long long t0 = clock64();
+  const int c2 = (tid * 2) & 255;
+  auto ld2 = [&](const __nv_bfloat16 (*m)[256], int j, float& a, float& b) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&m[j][c2]);
+    a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
+  };
+  float u0, u1, r0, r1;
+  ld2(usm, 0, u0, u1); ld2(dsm, 0, r0, r1);
+  float d0 = S0.delta(r0), d1 = S1.delta(r1);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+    for (int j = 0; j < 16; j += 4) {
+      float y0[4], y1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int jn = (j + k + 1) & 15;
+        float un0, un1, rn0, rn1;
+        ld2(usm, jn, un0, un1); ld2(dsm, jn, rn0, rn1);
+        const float dn0 = S0.delta(rn0), dn1 = S1.delta(rn1);
+        y0[k] = S0.template step<0>(d0, d0 * u0, 0.5f * u0, &bc[j + k][0]);
+        y1[k] = S1.template step<0>(d1, d1 * u1, 0.5f * u1, &bc[j + k][0]);
+        u0 = un0; u1 = un1; d0 = dn0; d1 = dn1;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<float2*>(&ys[k][tid * 2]) = make_float2(y0[k], y1[k]);
+    }
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+  float acc = 0;
+  for (int j = 0; j < 4; ++j) acc += ys[j][tid];
+  if (acc == 12345.678f) out[0] = acc;
+}
+
+template <int WARPS, int MINB>
+void run2ch(const char* name) {
+  cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
+  const int blocks = pr.multiProcessorCount * MINB;
+  float* out; long long* cyc; cudaMalloc(&out, 4); cudaMalloc(&cyc, blocks * 8);
+  const int iters = 400;
+  k2ch<WARPS, MINB><<<blocks, WARPS * 32>>>(out, cyc, 10);
+  cudaDeviceSynchronize();
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  k2ch<WARPS, MINB><<<blocks, WARPS * 32>>>(out, cyc, iters);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  cudaError_t err = cudaGetLastError();
+  // channel-steps per SMSP: 2 per thread-step
+  const double chsteps_per_smsp = 2.0 * 16.0 * iters * WARPS * MINB / 4.0;
+  int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+  printf("%-34s warps/SM=%2d 2 channels/thread : %.3f ms = %7.1f cyc per (warp, channel)-step per SMSP at %.2f GHz (%s)\n", name,
+         WARPS * MINB, ms, ms * 1e-3 * clk * 1e3 / chsteps_per_smsp, clk / 1e6, cudaGetErrorString(err));
+  cudaFree(out); cudaFree(cyc);
+}
+
 template <int NL, int NH, int WARPS, bool SOFTPLUS>
 void run(const char* name, int mod, int thr) {
   cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
@@ -212,6 +290,10 @@ int main() {
   run<0, 4, 24, true>("3 of 7 warps 4-pair", 7, 3);
   run<1, 4, 24, true>("1 pair everywhere, 3 of 7 warps 4-pair", 7, 3);
   run<1, 3, 24, true>("1 pair everywhere, 3 of 7 warps 3-pair", 7, 3);
+  run2ch<16, 1>("2 ch/thread, 16 warps (128 regs)");
+  run2ch<8, 2>("2 ch/thread, 2 x 8 warps");
+  run2ch<12, 1>("2 ch/thread, 12 warps (168 regs)");
+  run2ch<4, 4>("2 ch/thread, 4 x 4 warps");
   runp<0, 16, 1>("pipelined, 16 warps (128 regs)");
   runp<1, 16, 1>("pipelined, 16 warps (128 regs)");
   runp<2, 16, 1>("pipelined, 16 warps (128 regs)");
