@@ -5,10 +5,13 @@
 //   [EXT] mamba_ssm selective_scan_fn(u, delta, A, B, C, D, z, delta_bias, delta_softplus=True)
 //   [EXT] Caduceus BiMambaWrapper.forward: mamba_fwd(u) + flip_L(mamba_rev(flip_L(u)))
 //
-// Work decomposition: one CTA = one sequence x 128 channels; 256 threads: warps 0-3 run the forward scan,
-// warps 4-7 the reverse scan, one thread = one (direction, channel) holding its 16 fp32 states and 16 A
-// coefficients in registers.  (Keeping both directions in one thread needs ~126 registers, i.e. 4 warps per
-// scheduler, and the kernel is latency-bound there; one direction per thread fits 6 warps per scheduler.)
+// Work decomposition: one CTA = one sequence x 64 channels; 128 threads: warps 0-1 run the forward scan, warps 2-3
+// the reverse scan, one thread = one (direction, channel) holding its 16 fp32 states and 16 A coefficients in
+// registers.  Measured on B200 (l32, B = 256, ms per launch): 128 channels x 3 CTAs/SM (80 registers, 24 warps/SM)
+// 5.16; 128 x 2 CTAs (128 registers) 5.08; 64 channels x 5 CTAs (96 registers) 4.94; 64 x 4 CTAs (124 registers)
+// 4.89, and 4.79 with 8-step blocks.  Smaller blocks mean more independently phased blocks per SM (the chunk phases of
+// one block overlap the main loops of the others, and a barrier waits for 4 warps, not 8); 124 registers let the
+// compiler keep a whole 8-step block in flight.  16 warps/SM are enough: the step is MUFU-bound, not latency-bound.
 // Step i advances the forward scan at t_f = i and the reverse scan at t_r = L-1-i.  Inputs are streamed in chunks
 // of 16 steps by TMA (3-D tensor maps, one issuing thread, 2-stage mbarrier ring: see biscan_kernel); the 32 B/C
 // values per step are converted to fp32 once per chunk and broadcast-read.  Each thread leaves its un-gated y for
@@ -24,7 +27,7 @@
 //     that d = d' ln 2 owes to the input term is folded into B when B is converted;
 // (c) softplus costs one MUFU op, not two: log2(1 + e), e = 2^-|x| in (0, 1], is a 7-coefficient FMA-pipe polynomial
 //     (PCAD_SCAN_SPPOLY), and it runs one step ahead of the recurrence;
-// (d) the main loop advances in blocks of 4 steps whose shared-memory stores are deferred to the end of the block, so
+// (d) the main loop advances in blocks of 8 steps whose shared-memory stores are deferred to the end of the block, so
 //     the scheduler overlaps one step's tail with the next step's loads (and the state-register copies of a 1-step
 //     loop disappear);
 // (e) every instruction outside the main loop counts (the kernel issues at ~0.65 IPC): loads are TMA, the B|C
@@ -48,7 +51,11 @@ namespace pcad {
 #define PCAD_SCAN_TC 16
 #endif
 constexpr int kScanTC = PCAD_SCAN_TC;      // timesteps per chunk
-constexpr int kScanCH = 128;     // channels per CTA
+#ifndef PCAD_SCAN_CH
+#define PCAD_SCAN_CH 64
+#endif
+constexpr int kScanCH = PCAD_SCAN_CH;     // channels per CTA (128, or 64: smaller blocks, more of them per SM)
+constexpr int kScanSeg8 = kScanCH / 8;    // 8-channel (16-byte bf16) segments per row
 constexpr int kScanThreads = 2 * kScanCH;
 constexpr int kScanN = 16;       // d_state
 #ifndef PCAD_SCAN_POLY
@@ -59,9 +66,12 @@ constexpr int kScanPoly = PCAD_SCAN_POLY;   // pairs (of 8) whose exp2 runs on t
 #define PCAD_SCAN_SPPOLY 7   // 0: softplus through MUFU.EX2 + MUFU.LG2; 6 / 7: log2(1 + e) from a polynomial with that many coefficients
 #endif
 #ifndef PCAD_SCAN_UNROLL
-#define PCAD_SCAN_UNROLL 4
+#define PCAD_SCAN_UNROLL 8
 #endif
-constexpr int kScanUnroll = PCAD_SCAN_UNROLL;   // main-loop unroll (2 removes the state-register copies)
+constexpr int kScanUnroll = PCAD_SCAN_UNROLL;   // steps per main-loop block (stores deferred to the end of the block)
+#ifndef PCAD_SCAN_MINBLOCKS64
+#define PCAD_SCAN_MINBLOCKS64 4   // 64-channel blocks (128 threads, 41 KB): 4 per SM leave 128 registers per thread (124 used)
+#endif
 #ifndef PCAD_SCAN_MINBLOCKS
 #define PCAD_SCAN_MINBLOCKS 3
 #endif
@@ -241,7 +251,7 @@ template <> struct ScanDir<false> {
 // memory to stage them, so every chunk re-reads them from L2 and the warp waits out that latency with the MUFU pipe idle
 // (block order does not change it).  Opt-in (PCAD_FUSED_DT=1); it belongs with a 2-CTA/SM layout.
 template <typename T, bool PRECISE, bool DFINAL, bool ZGATED, bool FUSEDT>
-__global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : PCAD_SCAN_MINBLOCKS)
+__global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : (kScanCH == 64 ? PCAD_SCAN_MINBLOCKS64 : PCAD_SCAN_MINBLOCKS))
 biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__ CUtensorMap tm_df,
               const __grid_constant__ CUtensorMap tm_bcf, const __grid_constant__ CUtensorMap tm_ur,
               const __grid_constant__ CUtensorMap tm_dr, const __grid_constant__ CUtensorMap tm_bcr,
@@ -263,7 +273,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   __shared__ __align__(8) uint64_t full_bar[2];
 
   const int tid = threadIdx.x;
-  const int dir = tid >> 7;               // warp-uniform: warps 0-3 forward, 4-7 reverse
+  const int dir = tid / kScanCH;          // warp-uniform: the first half of the warps runs forward, the second half reverse
   const int ch = tid & (kScanCH - 1);
   const int e0 = blockIdx.x * kScanCH;
   const int e = e0 + ch;
@@ -327,7 +337,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
       // (16-byte chunk c of row r sits at chunk c ^ (r & 7)); B-fragments straight from global / L2 in the
       // per-lane order prep_dt_weight_kernel left them in (32 contiguous bytes per channel and lane quarter).
       const int lane = tid & 31, g = lane >> 2, q = lane & 3;
-      const int wch0 = ((tid >> 5) & 3) * 32;
+      const int wch0 = ((tid >> 5) % (kScanCH / 32)) * 32;
       const uint8_t* dtile = reinterpret_cast<const uint8_t*>(&s.dt[dir][0][0]);
       uint32_t afr[4][4];
 #pragma unroll
@@ -363,9 +373,9 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     }
     // B|C to fp32, once per chunk, 4 values per thread (B carries the ln 2 of the log2-domain delta on the fast
     // path); the reverse direction's rows are un-flipped here so that the main loop indexes both alike
-    {
-      static_assert(2 * kScanTC * 2 * kScanN == 4 * kScanThreads, "one 4-value group per thread");
-      const int dd = tid >> 7, r = tid & 127;
+#pragma unroll
+    for (int gi = tid; gi < 2 * kScanTC * 2 * kScanN / 4; gi += kScanThreads) {   // 256 groups of 4 values
+      const int dd = gi >> 7, r = gi & 127;
       const int j = r >> 3, k0 = (r & 7) * 4;
       const T* src = &s.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
       float4 v;
@@ -386,7 +396,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     const bool late_chunk = (L - 1 - i0) < i0;   // every position of the chunk was parked in an earlier chunk
     if (sizeof(T) == 2 && late_chunk) {
       // block-uniform fast path (bf16): one (step, segment) item per thread and direction, no per-item classification
-      const int j = tid >> 4, seg = tid & 15;
+      const int j = tid / kScanSeg8, seg = tid % kScanSeg8;
       const int chn = e0 + seg * 8;
       if (j < nsteps && chn < E) {
         const long long rf = row0 + i0 + j, rr = row0 + (L - 1 - i0 - j);
@@ -467,8 +477,8 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
       // in an earlier chunk ("late").  No per-item branching, packed fp32x2 arithmetic for the add and the gate.
       const bool early = !has_final, late = late_chunk;
       if (early || late) {
-        static_assert(kScanTC * (kScanCH / 8) == kScanThreads, "one item per thread and direction");
-        const int j = tid >> 4, seg = tid & 15;
+        static_assert(kScanTC * kScanSeg8 == kScanThreads, "one item per thread and direction");
+        const int j = tid / kScanSeg8, seg = tid % kScanSeg8;
         const int chn = e0 + seg * 8;
         if (j < nsteps && chn < E) {
 #pragma unroll
