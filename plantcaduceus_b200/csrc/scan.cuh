@@ -246,10 +246,10 @@ template <> struct ScanDir<false> {
 // [EXT Mamba.dt_proj, F.linear(dt, W)] runs inside the scan, one 16 x 32 x 64 product per warp and chunk, its fp32
 // accumulators rounded to bf16 exactly where the GEMM would have rounded them -- the two dt_proj launches of a layer
 // and the 4 KB per token of delta they write and the scan re-reads disappear.  Measured on B200 (l32, B = 256): the
-// dt_proj stage goes away (-12.5 ms per step) and the SM clock rises (less HBM traffic under the power cap), but the scan
-// grows by 30 ms: at 3 CTAs/SM there are neither the 32 registers to keep the weight fragments nor the 32 KB of shared
-// memory to stage them, so every chunk re-reads them from L2 and the warp waits out that latency with the MUFU pipe idle
-// (block order does not change it).  Opt-in (PCAD_FUSED_DT=1); it belongs with a 2-CTA/SM layout.
+// dt_proj stage goes away (-12 ms per step) and the SM clock rises (less HBM traffic under the power cap), but the scan
+// grows by 21 ms (30 with 128-channel blocks): the weight fragments fit neither the registers nor the shared memory
+// that 4 blocks/SM leave, so every chunk re-reads them from L2 and the warp waits out that latency with the MUFU pipe
+// idle (block order does not change it).  Opt-in (PCAD_FUSED_DT=1).
 template <typename T, bool PRECISE, bool DFINAL, bool ZGATED, bool FUSEDT>
 __global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : (kScanCH == 64 ? PCAD_SCAN_MINBLOCKS64 : PCAD_SCAN_MINBLOCKS))
 biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__ CUtensorMap tm_df,
