@@ -94,6 +94,19 @@ int pcad_forward(pcad_handle* h, const int64_t* ids_dev, int B, int L,
 int pcad_score_masked(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos_dev,
                       int B, int L, int n_mask, float* logits4_dev, void* stream);
 
+/* Replaces: model(input_ids, output_hidden_states=True).hidden_states[-1][:, tokenIdx, :]  (extract_embeddings,
+ * train_XGBoost.py:104-105) without materialising [B, L, 2*d_model]: ids_dev uint8 [B, L] (masked or not, as the caller
+ * wants), pos_dev int32 [B, n_pos]; hidden_dev receives [B, n_pos, 2*d_model] in the model dtype (forward half, then the
+ * RC half with its channels in the reference's order -- the caller's `reverse[..., ::-1]` average applies as is). */
+int pcad_hidden_at(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos_dev, int B, int L, int n_pos,
+                   void* hidden_dev, void* stream);
+
+/* Token ids outside [0, vocab_size) (the reference's nn.Embedding would raise) are detected on the device by
+ * pcad_forward / pcad_score_masked: the offending position is scored as id 0 and a flag is raised in mapped host
+ * memory.  pcad_take_id_error returns PCAD_ERR_INVALID and clears the flag if any call since the last take saw such an
+ * id, PCAD_OK otherwise; sync != 0 synchronises `stream` first, so the answer covers every call enqueued on it. */
+int pcad_take_id_error(pcad_handle* h, void* stream, int sync);
+
 /* End-to-end host entry (SequenceDataset.__getitem__ + extract_logits, zero_shot_score.py:49-62,
  * 107-121): ascii_host = B windows of L ASCII bases (pinned memory recommended); position token_idx
  * of every window is masked; logits4_host receives float32 [B, 4] (a,c,g,t).  Copies H2D, tokenises

@@ -18,7 +18,7 @@ STAGES = ("embed", "norm", "in_proj", "conv", "x_proj", "dt_proj", "scan", "out_
 
 EXPORTS = (
     "pcad_abi_version", "pcad_create", "pcad_destroy", "pcad_last_error", "pcad_set_weight", "pcad_finalize",
-    "pcad_set_tokenizer", "pcad_forward", "pcad_score_masked", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
+    "pcad_set_tokenizer", "pcad_take_id_error", "pcad_hidden_at", "pcad_forward", "pcad_score_masked", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
     "pcad_workspace_bytes", "pcad_set_profiling", "pcad_get_profile", "pcad_launch_count",
     "pcad_op_linear", "pcad_op_linear_softplus", "pcad_op_linear_residual", "pcad_op_linear_rowscale", "pcad_op_linear_rowscale_silu", "pcad_op_sumsq_parts",
     "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_conv_xproj", "pcad_op_biscan", "pcad_op_biscan_dt", "pcad_op_prep_dt_weight",
@@ -61,6 +61,8 @@ def load() -> C.CDLL:
     lib.pcad_set_weight.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32, i32]
     lib.pcad_finalize.argtypes = [vp]
     lib.pcad_set_tokenizer.argtypes = [vp, C.POINTER(C.c_uint8), i32, C.POINTER(C.c_int32)]
+    lib.pcad_take_id_error.argtypes = [vp, vp, i32]
+    lib.pcad_hidden_at.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.pcad_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     lib.pcad_score_masked.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.pcad_score_windows_host.argtypes = [vp, vp, i32, i32, i32, vp, vp]

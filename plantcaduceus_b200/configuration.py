@@ -104,8 +104,15 @@ class CaduceusConfig:
             bad.append("ssm_cfg.bias=True")
         if not self.ssm_cfg.get("conv_bias", True):
             bad.append("ssm_cfg.conv_bias=False")
-        if self.d_model % 64 != 0:
-            bad.append(f"d_model={self.d_model} not a multiple of 64")
+        # the engine's own limits (pcad_create, csrc/pcad.cu): reject here instead of failing later at .to("cuda")
+        if self.d_model % 128 != 0 or not (0 < self.d_model <= 2048):
+            bad.append(f"d_model={self.d_model} (engine needs a multiple of 128, <= 2048)")
+        if self.expand != 2:
+            bad.append(f"expand={self.expand} (engine is specialised for 2)")
+        if self.dt_rank <= 0 or self.dt_rank % 8 != 0:
+            bad.append(f"dt_rank={self.dt_rank} (engine needs a multiple of 8)")
+        if not self.fused_add_norm:
+            bad.append("fused_add_norm=False (different module tree, key names and rounding order)")
         if self.vocab_size != 8:
             bad.append(f"vocab_size={self.vocab_size} (engine LM head is specialised for 8 rows)")
         if bad:

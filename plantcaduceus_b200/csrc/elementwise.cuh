@@ -92,6 +92,16 @@ __global__ void ids64_to_u8_kernel(const long long* __restrict__ in, uint8_t* __
   out[i] = static_cast<uint8_t>(v);
 }
 
+// uint8 ids from the caller (pcad_score_masked): same validation, no widening
+__global__ void ids_u8_check_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long n, int V,
+                                    int* __restrict__ bad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t v = in[i];
+  if (v >= V) { atomicExch(bad, 1); out[i] = 0; return; }
+  out[i] = v;
+}
+
 // ---- RC-aware embedding [EXT RCPSEmbedding.forward] --------------------------------------------
 // out[s*L + t, :] = emb[id_s[t], :]  (see layout note above).  One thread per 8 channels.
 template <typename T>
@@ -391,6 +401,36 @@ __global__ void hidden_tap_kernel(const T* __restrict__ H, T* __restrict__ out, 
     for (int i = 0; i < 8; ++i) x[i] = y[7 - i];
   }
   store8<T>(out + bt * (2 * d) + j0, x);
+}
+
+// The same tap at requested positions only (reference train_XGBoost.py:105: hidden_states[-1][:, tokenIdx, :]):
+// out[b, i, :] = hidden_states[-1][b, pos[b*n_pos + i], :], without materialising [B, L, 2d].  Invalid positions give NaN.
+template <typename T>
+__global__ void hidden_tap_pos_kernel(const T* __restrict__ H, const int* __restrict__ pos, int n_pos, T* __restrict__ out,
+                                      int B, int L, int d) {
+  const int vec_per_row = (2 * d) / 8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * n_pos * vec_per_row;
+  if (gid >= total) return;
+  const int v = static_cast<int>(gid % vec_per_row);
+  const long long item = gid / vec_per_row;
+  const int b = static_cast<int>(item / n_pos);
+  const int t = pos[item];
+  const int j0 = v * 8;
+  float x[8];
+  if (t < 0 || t >= L) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __int_as_float(0x7fc00000);
+  } else if (j0 < d) {
+    load8<T>(H + (static_cast<long long>(b) * L + t) * d + j0, x);
+  } else {
+    const int jj = j0 - d;
+    float y[8];
+    load8<T>(H + (static_cast<long long>(B + b) * L + (L - 1 - t)) * d + (d - 8 - jj), y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = y[7 - i];
+  }
+  store8<T>(out + item * (2 * d) + j0, x);
 }
 
 }  // namespace pcad

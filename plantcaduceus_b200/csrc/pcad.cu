@@ -88,7 +88,8 @@ struct pcad_handle {
   uint8_t* comp_dev = nullptr;   // [V]
   uint8_t* lut_dev = nullptr;    // [256]
   int* sel_dev = nullptr;        // [4] acgt ids
-  int* bad_flag = nullptr;       // device flag for out-of-range ids
+  int* bad_flag = nullptr;       // out-of-range-id flag: device alias of bad_flag_host (mapped pinned memory)
+  volatile int* bad_flag_host = nullptr;
   int mask_id = 1;
   int acgt[4] = {3, 4, 5, 6};
   Workspace ws;
@@ -628,7 +629,19 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   rc |= dev_alloc(h, &h->comp_dev, 16);
   rc |= dev_alloc(h, &h->lut_dev, 256);
   rc |= dev_alloc(h, &h->sel_dev, 4);
-  rc |= dev_alloc(h, &h->bad_flag, 1);
+  {
+    // zero-copy flag: the id-validation kernels set it, pcad_take_id_error reads it without a device copy
+    void* hp = nullptr;
+    void* dp = nullptr;
+    if (cudaHostAlloc(&hp, sizeof(int), cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) {
+      if (hp) cudaFreeHost(hp);
+      rc |= fail(h, PCAD_ERR_NOMEM, "cudaHostAlloc for the id-error flag failed");
+    } else {
+      h->bad_flag_host = static_cast<volatile int*>(hp);
+      *h->bad_flag_host = 0;
+      h->bad_flag = static_cast<int*>(dp);
+    }
+  }
   for (auto& lw : h->layers) {
     rc |= A8(&lw.in_proj, static_cast<size_t>(2) * h->E * h->d * a);
     if (h->fuse_norm) rc |= A8(&lw.in_proj_s, static_cast<size_t>(2) * h->E * h->d * a);
@@ -656,7 +669,6 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   uint8_t comp8[16] = {0};
   for (int i = 0; i < h->V; ++i) comp8[i] = static_cast<uint8_t>(cfg->complement_map[i]);
   cudaMemcpy(h->comp_dev, comp8, 16, cudaMemcpyHostToDevice);
-  cudaMemset(h->bad_flag, 0, sizeof(int));
   // default tokenizer tables: [PAD]=0 [MASK]=1 [UNK]=2 a=3 c=4 g=5 t=6, case-folded, everything else UNK
   uint8_t lut[256];
   memset(lut, 2, sizeof(lut));
@@ -673,6 +685,7 @@ void pcad_destroy(pcad_handle* h) {
   for (auto& pe : h->prof_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
   for (auto ev : h->event_pool) cudaEventDestroy(ev);
   if (h->ws.base) cudaFree(h->ws.base);
+  if (h->bad_flag_host) cudaFreeHost(const_cast<int*>(h->bad_flag_host));
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -742,12 +755,13 @@ int pcad_set_weight(pcad_handle* h, const char* name, const void* data, const in
   int rc;
   if (leaf == "in_proj.weight") {
     if (!shape_is(shape, ndim, {2 * E, d})) return bad_shape();
-    if (dir == 1) return PCAD_OK;  // tied to mamba_fwd (bidirectional_weight_tie)
+    // tied to mamba_fwd (bidirectional_weight_tie); a de-duplicated checkpoint may carry only the mamba_rev name
+    if (dir == 1 && lw.has_in) return PCAD_OK;
     rc = ingest(h, data, src_dtype, lw.in_proj, h->f32, 2LL * E * d);
     lw.has_in = rc == PCAD_OK;
   } else if (leaf == "out_proj.weight") {
     if (!shape_is(shape, ndim, {d, E})) return bad_shape();
-    if (dir == 1) return PCAD_OK;
+    if (dir == 1 && lw.has_out) return PCAD_OK;
     rc = ingest(h, data, src_dtype, lw.out_proj, h->f32, static_cast<long long>(d) * E);
     lw.has_out = rc == PCAD_OK;
   } else if (leaf == "conv1d.weight") {
@@ -930,10 +944,42 @@ int pcad_score_masked(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = ensure_workspace(h, B, L);
   if (rc) return rc;
-  CUDA_TRY(h, cudaMemcpyAsync(h->ws.ids, ids_dev, static_cast<size_t>(B) * L, cudaMemcpyDeviceToDevice, st));
+  {
+    // copy + validate: ids >= vocab_size would index past the embedding table / complement map
+    StageTimer tm(h, st, PCAD_ST_MISC);
+    const long long n = static_cast<long long>(B) * L;
+    ids_u8_check_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ids_dev, h->ws.ids, n, h->V, h->bad_flag);
+    CUDA_TRY(h, cudaGetLastError());
+  }
   rc = run_backbone(h, B, L, st);
   if (rc) return rc;
   return run_head(h, B, L, pos_dev, n_mask, logits4_dev, st);
+}
+
+int pcad_hidden_at(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos_dev, int B, int L, int n_pos, void* hidden_dev, void* stream) {
+  int rc = check_call(h, B, L);
+  if (rc) return rc;
+  if (B == 0 || L == 0 || n_pos == 0) return PCAD_OK;
+  if (!ids_dev || !pos_dev || !hidden_dev || n_pos < 0) return fail(h, PCAD_ERR_INVALID, "null or negative argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B, L);
+  if (rc) return rc;
+  {
+    StageTimer tm(h, st, PCAD_ST_MISC);
+    const long long n = static_cast<long long>(B) * L;
+    ids_u8_check_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ids_dev, h->ws.ids, n, h->V, h->bad_flag);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  rc = run_backbone(h, B, L, st);
+  if (rc) return rc;
+  StageTimer tm(h, st, PCAD_ST_MISC);
+  const long long total = static_cast<long long>(B) * n_pos * (2 * h->d / 8);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (h->f32) hidden_tap_pos_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(h->ws.normed), pos_dev, n_pos, static_cast<float*>(hidden_dev), B, L, h->d);
+  else hidden_tap_pos_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(h->ws.normed), pos_dev, n_pos, static_cast<bf16*>(hidden_dev), B, L, h->d);
+  CUDA_TRY(h, cudaGetLastError());
+  return PCAD_OK;
 }
 
 int pcad_score_windows_host(pcad_handle* h, const uint8_t* ascii_host, int B, int L, int token_idx, float* logits4_host, void* stream) {
@@ -961,6 +1007,19 @@ int pcad_score_windows_host(pcad_handle* h, const uint8_t* ascii_host, int B, in
   if (rc) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(logits4_host, ws.logits4, static_cast<size_t>(B) * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
+  return PCAD_OK;
+}
+
+int pcad_take_id_error(pcad_handle* h, void* stream, int sync) {
+  if (!h) return PCAD_ERR_INVALID;
+  if (sync) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  }
+  if (h->bad_flag_host && *h->bad_flag_host) {
+    *h->bad_flag_host = 0;
+    return fail(h, PCAD_ERR_INVALID, "token id outside [0, %d) in an earlier pcad_forward / pcad_score_masked call (the row was scored with id 0)", h->V);
+  }
   return PCAD_OK;
 }
 

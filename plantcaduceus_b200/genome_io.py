@@ -24,27 +24,37 @@ def _open_text(path: str):
 # ---------------------------------------------------------------------------------------------------
 # FASTA
 # ---------------------------------------------------------------------------------------------------
+def _open_bytes(path: str):
+    return gzip.open(path, "rb") if str(path).endswith(".gz") else open(path, "rb")
+
+
+_WHITESPACE = np.zeros(256, dtype=bool)
+_WHITESPACE[[9, 10, 11, 12, 13, 32]] = True
+
+
 def read_fasta(path: str) -> Dict[str, bytes]:
     """{record id: sequence bytes}.  The id is the header up to the first whitespace, which is the key
-    ``SeqIO.to_dict`` uses (reference src/zero_shot_score.py:176-180)."""
+    ``SeqIO.to_dict`` uses (reference src/zero_shot_score.py:176-180).  The file is read once as bytes and each record's
+    line breaks are removed with one vectorised mask (a per-line Python loop is minutes on a plant genome)."""
+    with _open_bytes(path) as f:
+        data = f.read()
+    arr = np.frombuffer(data, dtype=np.uint8)
     out: Dict[str, bytes] = {}
-    name: Optional[str] = None
-    chunks: List[bytes] = []
-    with _open_text(path) as f:
-        for line in f:
-            if line.startswith(">"):
-                if name is not None:
-                    out[name] = b"".join(chunks)
-                name = line[1:].split()[0] if len(line) > 1 and line[1:].split() else ""
-                if name in out:
-                    raise ValueError(f"duplicate FASTA record id {name!r}")
-                chunks = []
-            else:
-                s = line.strip()
-                if s:
-                    chunks.append(s.encode("ascii"))
-    if name is not None:
-        out[name] = b"".join(chunks)
+    if arr.size == 0:
+        return out
+    nl = np.flatnonzero(arr == 10)
+    starts = np.concatenate(([0], nl + 1))
+    starts = starts[starts < arr.size]
+    hdr = starts[arr[starts] == ord(">")]
+    for k, h in enumerate(hdr):
+        j = np.searchsorted(nl, h)
+        eol = int(nl[j]) if j < len(nl) else arr.size
+        fields = data[h + 1:eol].split()
+        name = fields[0].decode("ascii") if fields else ""
+        if name in out:
+            raise ValueError(f"duplicate FASTA record id {name!r}")
+        body = arr[min(eol + 1, arr.size):int(hdr[k + 1]) if k + 1 < len(hdr) else arr.size]
+        out[name] = body[~_WHITESPACE[body]].tobytes()
     return out
 
 

@@ -73,6 +73,11 @@ class CaduceusForMaskedLM:
                 sd = load_file(st)
             else:
                 sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
+            # safetensors checkpoints are saved with tied tensors de-duplicated: restore the embedding <-> LM head tie
+            # (the mamba_fwd / mamba_rev projection tie is resolved by the engine, whichever name survived)
+            from .weights import EMB_KEY, HEAD_KEY
+            if EMB_KEY not in sd and HEAD_KEY in sd:
+                sd[EMB_KEY] = sd[HEAD_KEY]
             return cls(cfg, sd, torch_dtype, CharDNATokenizer.from_pretrained(path))
         raise FileNotFoundError(
             f"{path!r} is not a local checkpoint directory (no network here). Use from_random('{path}') for "
@@ -148,8 +153,19 @@ class CaduceusForMaskedLM:
         _lib.check(self._lib.pcad_create(C.byref(pc), self.device.index, C.byref(h)))
         self._handle = h
         try:
+            comp_want = [int(cfg.complement_map.get(i, i)) for i in range(cfg.vocab_size)]
             for name, t in self._sd.items():
                 src = t.detach()
+                # HF checkpoints carry the RCPS modules' persistent integer buffers ([EXT] RCPSEmbedding / RCPSLMHead
+                # register_buffer("complement_map")): not weights.  They must agree with config.complement_map, which
+                # is what the engine was created with.
+                if name.endswith("complement_map"):
+                    got = [int(x) for x in src.flatten().tolist()]
+                    if got[:cfg.vocab_size] != comp_want[:len(got)]:
+                        raise ValueError(f"{name} = {got} disagrees with config.complement_map = {comp_want}")
+                    continue
+                if not src.is_floating_point():
+                    continue
                 # Weights are rounded to the model dtype exactly as from_pretrained(torch_dtype=...) would.
                 # (that cast covers A_log and D too; Mamba then reads them back with .float()).
                 if src.dtype != self.dtype and src.is_floating_point():
@@ -203,13 +219,23 @@ class CaduceusForMaskedLM:
                     self._handle, C.c_void_p(ids.data_ptr()), B, L,
                     C.c_void_p(logits.data_ptr()) if logits is not None else None,
                     C.c_void_p(hidden.data_ptr()) if hidden is not None else None, self._stream()), self._handle)
+                self._raise_on_bad_ids(True)
         # hidden_states: only the final (normed) state is materialised; hidden_states[-1] is what the
         # reference's callers read (train_XGBoost.py:105, notebooks/examples.ipynb:183).
         return MaskedLMOutput(logits=logits, hidden_states=(hidden,) if hidden is not None else None)
 
-    def score_masked(self, ids_u8: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+    def _raise_on_bad_ids(self, sync: bool):
+        """Token ids outside [0, vocab_size) raise IndexError, as the reference's nn.Embedding lookup would
+        (the engine validates on the device; ``sync`` waits for the stream so the answer covers this call)."""
+        rc = self._lib.pcad_take_id_error(self._handle, self._stream(), int(sync))
+        if rc != 0:
+            msg = self._lib.pcad_last_error(self._handle)
+            raise IndexError(msg.decode() if msg else "token id out of range")
+
+    def score_masked(self, ids_u8: torch.Tensor, positions: torch.Tensor, check_ids: bool = True) -> torch.Tensor:
         """ids_u8: uint8 [B, L] token ids (already masked) on the device; positions: int32 [B, n_mask].
-        Returns float32 [B, n_mask, 4] logits in a,c,g,t order (extract_logits / _masked_probs gather)."""
+        Returns float32 [B, n_mask, 4] logits in a,c,g,t order (extract_logits / _masked_probs gather).
+        ``check_ids=False`` keeps the call asynchronous: an out-of-range id is then reported by the next checking call."""
         self._require_handle()
         ids = ids_u8.to(device=self.device, dtype=torch.uint8).contiguous()
         pos = positions.to(device=self.device, dtype=torch.int32).contiguous()
@@ -222,6 +248,25 @@ class CaduceusForMaskedLM:
             if B > 0 and L > 0 and n_mask > 0:
                 _lib.check(self._lib.pcad_score_masked(self._handle, C.c_void_p(ids.data_ptr()), C.c_void_p(pos.data_ptr()),
                                                        B, L, n_mask, C.c_void_p(out.data_ptr()), self._stream()), self._handle)
+                self._raise_on_bad_ids(check_ids)
+        return out
+
+    def hidden_at(self, ids_u8: torch.Tensor, positions: torch.Tensor) -> torch.Tensor:
+        """``hidden_states[-1][b, positions[b, i], :]`` for uint8 ids [B, L]: [B, n_pos, 2*d_model] in the model dtype,
+        without materialising the full hidden state (reference extract_embeddings, train_XGBoost.py:104-105)."""
+        self._require_handle()
+        ids = ids_u8.to(device=self.device, dtype=torch.uint8).contiguous()
+        pos = positions.to(device=self.device, dtype=torch.int32).contiguous()
+        B, L = ids.shape
+        if pos.dim() == 1:
+            pos = pos[:, None]
+        n_pos = pos.shape[1]
+        with torch.cuda.device(self.device):
+            out = torch.empty((B, n_pos, 2 * self.config.d_model), dtype=self.dtype, device=self.device)
+            if B > 0 and L > 0 and n_pos > 0:
+                _lib.check(self._lib.pcad_hidden_at(self._handle, C.c_void_p(ids.data_ptr()), C.c_void_p(pos.data_ptr()),
+                                                    B, L, n_pos, C.c_void_p(out.data_ptr()), self._stream()), self._handle)
+                self._raise_on_bad_ids(True)
         return out
 
     def score_windows_host(self, ascii_windows: Union[np.ndarray, torch.Tensor], token_idx: int,
@@ -257,13 +302,17 @@ class CaduceusForMaskedLM:
                                                           C.c_void_p(out.data_ptr()), self._stream()), self._handle)
         return out
 
-    def score_windows_device(self, ascii_dev: torch.Tensor, token_idx: int) -> torch.Tensor:
-        """``score_windows_host`` for windows already on the device: uint8 [B, L] -> float32 [B, 4] (device, async)."""
+    def score_windows_device(self, ascii_dev: torch.Tensor, token_idx: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``score_windows_host`` for windows already on the device: uint8 [B, L] -> float32 [B, 4] (device, async;
+        written into ``out`` when given: a contiguous float32 [B, 4] device tensor)."""
         self._require_handle()
         a = ascii_dev.to(device=self.device, dtype=torch.uint8).contiguous()
         B, L = a.shape
         with torch.cuda.device(self.device):
-            out = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+            if out is None:
+                out = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+            elif out.shape != (B, 4) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+                raise ValueError("out must be a contiguous float32 [B, 4] tensor on the model's device")
             if B > 0:
                 _lib.check(self._lib.pcad_score_windows_dev(self._handle, C.c_void_p(a.data_ptr()), B, L, int(token_idx),
                                                             C.c_void_p(out.data_ptr()), self._stream()), self._handle)

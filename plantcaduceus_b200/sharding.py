@@ -59,6 +59,34 @@ def gather_rows(local: torch.Tensor, n_total: int, dst: int = 0) -> Optional[tor
     return torch.cat(out, dim=0)
 
 
+def scatter_rows(rows: Optional[torch.Tensor], device: Optional[torch.device] = None, src: int = 0) -> torch.Tensor:
+    """Rank ``src`` holds a [n, k] tensor (the parsed input); every rank gets back its contiguous ``shard_range`` share,
+    so the input files are read once, not once per rank.  Other ranks pass ``None``."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return rows
+    rank, world = dist.get_rank(), dist.get_world_size()
+    meta = [None]
+    if rank == src:
+        meta = [(int(rows.shape[0]), tuple(rows.shape[1:]), rows.dtype)]
+    dist.broadcast_object_list(meta, src=src)
+    n, tail, dtype = meta[0]
+    device = device if device is not None else (rows.device if rows is not None else torch.device("cpu"))
+    max_rows = -(-n // world) if n else 0
+    mine = torch.empty((max_rows,) + tuple(tail), dtype=dtype, device=device)
+    parts = None
+    if rank == src:
+        parts = []
+        for r in range(world):
+            s, e = shard_range(n, r, world)
+            p = torch.zeros((max_rows,) + tuple(tail), dtype=dtype, device=device)
+            p[: e - s] = rows[s:e].to(device)
+            parts.append(p)
+    if max_rows:
+        dist.scatter(mine, parts, src=src)
+    s, e = shard_range(n, rank, world)
+    return mine[: e - s]
+
+
 def score_sharded(score_fn, ascii_windows: np.ndarray, device: Optional[torch.device] = None) -> np.ndarray:
     """Scores this rank's contiguous share of ``ascii_windows`` [n, L] with ``score_fn(uint8 [m, L]) -> float32 [m, 4]``
     and returns the full [n, 4] result on every rank."""

@@ -116,18 +116,34 @@ def create_dataloader(sequences, tokenizer, batch_size, tokenIdx):
 
 def extract_logits(model, dataloader, device, tokenIdx, tokenizer) -> np.ndarray:
     """softmax over the a,c,g,t logits at the masked index for every window -> float32 [n, 4]
-    (reference extract_logits, :107-121)."""
+    (reference extract_logits, :107-121).  Batches are double-buffered: while the GPU scores batch i from one pinned
+    staging buffer, the host packs batch i+1 into the other; results stay on the device until one copy at the end (the
+    reference synchronises and copies per batch, :119)."""
     import torch
     dataset, batch_size = dataloader
     logging.info("Extracting logits")
-    out = np.zeros((len(dataset), 4), dtype=np.float32)
-    for start, ascii_batch in dataset.ascii_batches(batch_size):
-        if tokenIdx >= ascii_batch.shape[1] or tokenIdx < -ascii_batch.shape[1]:
-            raise IndexError(f"tokenIdx {tokenIdx} is out of bounds for a window of length {ascii_batch.shape[1]}")
-        pinned = torch.from_numpy(ascii_batch).pin_memory()
-        logits4 = model.score_windows_host(pinned, tokenIdx % ascii_batch.shape[1]).numpy()
-        out[start:start + len(ascii_batch)] = gio.softmax4(logits4)
-    return out
+    n = len(dataset)
+    dev = model.device
+    logits = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+    ring = [None, None]          # (pinned host buffer, device buffer, event recorded after the H2D copy was consumed)
+    for k, (start, ascii_batch) in enumerate(dataset.ascii_batches(batch_size)):
+        b, L = ascii_batch.shape
+        if tokenIdx >= L or tokenIdx < -L:
+            raise IndexError(f"tokenIdx {tokenIdx} is out of bounds for a window of length {L}")
+        slot = ring[k & 1]
+        if slot is None or slot[0].shape[0] < b or slot[0].shape[1] != L:
+            slot = (torch.empty((max(b, batch_size), L), dtype=torch.uint8).pin_memory(),
+                    torch.empty((max(b, batch_size), L), dtype=torch.uint8, device=dev), torch.cuda.Event())
+        else:
+            slot[2].synchronize()      # the copy that last used this pinned buffer has completed
+        host, devbuf, ev = slot
+        host[:b].copy_(torch.from_numpy(ascii_batch))
+        with torch.cuda.device(dev):
+            devbuf[:b].copy_(host[:b], non_blocking=True)
+            ev.record()
+            model.score_windows_device(devbuf[:b], tokenIdx % L, out=logits[start:start + b])
+        ring[k & 1] = slot
+    return gio.softmax4(logits.cpu().numpy()) if n else np.zeros((0, 4), dtype=np.float32)
 
 
 def _allele_index(values) -> np.ndarray:
@@ -142,8 +158,9 @@ def zero_shot_score(snpDF, logits) -> List[float]:
 
 
 def seq_from_vcf(args) -> Tuple[np.ndarray, List[int], list, list]:
-    """Windows for every VCF record with an SNV ALT (reference :172-214).  Returns
-    (ASCII [n, 512], record indices, header lines, records)."""
+    """Windows for every VCF record with an SNV ALT (reference :172-214), built on the host.  Returns
+    (ASCII [n, 512], record indices, header lines, records).  ``main`` uses ``variants_from_vcf`` + device-side
+    extraction instead; this keeps the reference's function for callers that want the windows themselves."""
     logging.info(f"Reading input data from {args.inputVCF}")
     fasta = gio.read_fasta(args.inputFasta)
     header, records = gio.read_vcf(args.inputVCF)
@@ -156,6 +173,34 @@ def seq_from_vcf(args) -> Tuple[np.ndarray, List[int], list, list]:
     return windows, record_indices, header, records
 
 
+def variants_from_vcf(args):
+    """Rank 0's parse of the VCF + FASTA (reference :172-214) into coordinates instead of windows: returns
+    (chrom names, {name: bytes}, chrom_id int32 [n], pos0 int64 [n], record indices, header, records) for the records
+    that carry at least one SNV ALT.  The windows are cut on the device from the resident chromosome with the same
+    slice-and-pad rule (pcad_extract_windows)."""
+    logging.info(f"Reading input data from {args.inputVCF}")
+    fasta = gio.read_fasta(args.inputFasta)
+    header, records = gio.read_vcf(args.inputVCF)
+    names: List[str] = []
+    index = {}
+    chrom_id, pos0, record_indices = [], [], []
+    for rec in records:
+        if not rec.has_snv:
+            continue
+        if rec.chrom not in fasta:
+            print(f"VCF record {rec.index}: chromosome {rec.chrom!r} is not in the FASTA (check that chromosome names match)")
+            print("Check that VCF file is sorted and chromosome names match FASTA file.")
+            raise SystemExit(1)
+        if rec.chrom not in index:
+            index[rec.chrom] = len(names)
+            names.append(rec.chrom)
+        chrom_id.append(index[rec.chrom])
+        pos0.append(rec.pos - 1)
+        record_indices.append(rec.index)
+    seqs = {c: fasta[c] for c in names}
+    return names, seqs, np.asarray(chrom_id, dtype=np.int32), np.asarray(pos0, dtype=np.int64), record_indices, header, records
+
+
 def zero_shot_score_vcf(args, recordIndices, logits, header, records):
     logging.info("Calculating zero-shot scores")
     gio.write_scored_vcf(args.output, header, records, recordIndices, logits)
@@ -163,37 +208,61 @@ def zero_shot_score_vcf(args, recordIndices, logits, header, records):
 
 def main(argv: Optional[Sequence[str]] = None):
     import pandas as pd
-    logging.basicConfig(level=logging.INFO, format="%(asctime)s - %(levelname)s - %(message)s", datefmt="%Y-%m-%d %H:%M:%S")
-    args = parse_args(argv)
-    if args.inputDF is not None:
-        logging.info(f"Reading input data from {args.inputDF}")
-        snpDF = pd.read_csv(args.inputDF, delimiter="\t")
-        logging.info("Filtering out invalid SNPs")
-        valid = snpDF["ref"].isin(list(gio.NUCLEOTIDES)) & snpDF["alt"].isin(list(gio.NUCLEOTIDES))
-        logging.info(f"Filtered out {len(snpDF) - int(valid.sum())} invalid SNPs")
-        snpDF = snpDF[valid].copy()
-        sequences = snpDF["sequences"].tolist()
-    else:
-        windows, recordIndices, header, records = seq_from_vcf(args)
-        sequences = [bytes(r).decode("ascii") for r in windows]
-
-    # One process per GPU under torchrun: contiguous window ranges per rank, scores gathered to every rank
-    # (SURVEY.md 8e); a single process otherwise.
     import torch
 
-    from . import sharding
+    from . import genome_scan, sharding
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s - %(levelname)s - %(message)s", datefmt="%Y-%m-%d %H:%M:%S")
+    args = parse_args(argv)
+    # One process per GPU under torchrun: contiguous variant ranges per rank, scores gathered once at the end
+    # (SURVEY.md 8e); a single process otherwise.  Only rank 0 reads the input files.
     rank, local_rank, world = sharding.env_world()
     device = f"cuda:{local_rank}" if world > 1 else args.device
     if world > 1:
         torch.cuda.set_device(local_rank)
         sharding.init_process_group(device=torch.device(device))
-    lo, hi = sharding.shard_range(len(sequences), rank, world)
     model, tokenizer = load_model_and_tokenizer(args.model, device, args.dtype, args.seed)
-    logging.info("Creating data loader")
-    loader = create_dataloader(sequences[lo:hi], tokenizer, args.batchSize, args.tokenIdx)
-    logits = extract_logits(model, loader, device, args.tokenIdx, tokenizer)
+
+    snpDF = None
+    if args.inputDF is not None:
+        windows = None
+        ragged = [None]
+        if rank == 0:
+            logging.info(f"Reading input data from {args.inputDF}")
+            snpDF = pd.read_csv(args.inputDF, delimiter="\t")
+            logging.info("Filtering out invalid SNPs")
+            valid = snpDF["ref"].isin(list(gio.NUCLEOTIDES)) & snpDF["alt"].isin(list(gio.NUCLEOTIDES))
+            logging.info(f"Filtered out {len(snpDF) - int(valid.sum())} invalid SNPs")
+            snpDF = snpDF[valid].copy()
+            sequences = snpDF["sequences"].tolist()
+            if len({len(q) for q in sequences}) <= 1:
+                windows = torch.from_numpy(tokenizer.windows_to_ascii(sequences, len(sequences[0]) if sequences else 512))
+            else:      # ragged table (the reference never checks lengths): every rank gets the strings
+                ragged = [sequences]
+        if world > 1:
+            torch.distributed.broadcast_object_list(ragged, src=0)
+        if ragged[0] is not None:
+            lo, hi = sharding.shard_range(len(ragged[0]), rank, world)
+            mine, n_total = ragged[0][lo:hi], len(ragged[0])
+        else:
+            shard = sharding.scatter_rows(windows, device=torch.device(device)) if world > 1 else windows
+            mine = [bytes(r).decode("latin-1") for r in shard.cpu().numpy()]
+            n_meta = [len(windows) if rank == 0 else None]
+            if world > 1:
+                torch.distributed.broadcast_object_list(n_meta, src=0)
+            n_total = n_meta[0]
+        logging.info("Creating data loader")
+        loader = create_dataloader(mine, tokenizer, args.batchSize, args.tokenIdx)
+        logits = extract_logits(model, loader, device, args.tokenIdx, tokenizer)
+        if world > 1:
+            logits = sharding.gather_rows(torch.from_numpy(logits).to(device), n_total).cpu().numpy()
+    else:
+        parsed = variants_from_vcf(args) if rank == 0 else (None,) * 7
+        names, seqs, chrom_id, pos0, recordIndices, header, records = parsed
+        raw = genome_scan.score_variants_sharded(model, names, seqs, chrom_id, pos0, args.batchSize, args.tokenIdx, 512,
+                                                 device=torch.device(device))
+        logits = gio.softmax4(raw) if len(raw) else np.zeros((0, 4), dtype=np.float32)
+
     if world > 1:
-        logits = sharding.gather_rows(torch.from_numpy(logits).to(device), len(sequences)).cpu().numpy()
         torch.distributed.barrier()
         if rank != 0:
             torch.distributed.destroy_process_group()

@@ -145,3 +145,96 @@ def test_device_window_extraction_bit_exact_and_genome_scoring(cuda_device):
     host_windows = np.stack([np.frombuffer(gio.extract_window(chrom, int(p), 255), dtype=np.uint8) for p in pos])
     want = gio.softmax4(model.score_windows_host(torch.from_numpy(host_windows.copy()).pin_memory(), 255).numpy())
     assert np.array_equal(probs, want)
+
+
+def test_scan_region_equals_cli_on_the_vcf_it_emits(cuda_device, tmp_path):
+    """Region-level saturation mutagenesis with the reference pipeline's semantics (1_simulation.R:85-120 ->
+    zero_shot_score.py -input-vcf): every A/C/G/T position of the region gets its own centred window.  The scores equal,
+    bit for bit, what the drop-in CLI writes for the headerless VCF rows the scan emits (one forward per ROW there, one per
+    position here), including positions whose window is N-padded at the chromosome start and soft-masked / N bases that
+    the R script drops."""
+    from plantcaduceus_b200 import mutagenesis as mut, zero_shot_score as zs
+    from plantcaduceus_b200.modeling import CaduceusForMaskedLM
+    rng = np.random.default_rng(17)
+    chrom = bytearray(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=1400).tobytes())
+    chrom[30:34] = b"acgt"      # soft-masked: dropped by `ref %in% c("A","C","G","T")`
+    chrom[50] = ord("N")
+    chrom = bytes(chrom)
+    fasta = tmp_path / "genome.fa"
+    fasta.write_text(">chrT test\n" + "\n".join(chrom[i:i + 60].decode() for i in range(0, len(chrom), 60)) + "\n")
+    cfg = CaduceusConfig(d_model=128, n_layer=2)
+    ckpt_model = CaduceusForMaskedLM.from_random(cfg, seed=0, torch_dtype=torch.float32).to(cuda_device)
+    res = mut.scan_region(ckpt_model, chrom, 20, 139, batch_size=50)
+    n_pos = 120 - 4 - 1
+    assert len(res["positions"]) == n_pos and len(res["pos"]) == 3 * n_pos
+    assert res["pos"].tolist() == sorted(res["pos"].tolist())
+    assert all(r != a for r, a in zip(res["ref"], res["alt"]))
+    assert 31 not in res["positions"] and 51 not in res["positions"]
+    vcf_in, vcf_out = str(tmp_path / "cand.vcf"), str(tmp_path / "scored.vcf")
+    mut.write_candidate_vcf(vcf_in, "chrT", res)
+    first = open(vcf_in).readline().rstrip("\n").split("\t")
+    assert len(first) == 7 and first[2] == "." and first[5] == "." and first[6] == "."
+    # the CLI builds its model from the same preset + seed; -model takes a directory or a preset, so go through a directory
+    import json, os
+    from safetensors.torch import save_file
+    ck = tmp_path / "ckpt"
+    os.makedirs(ck)
+    json.dump(cfg.to_dict(), open(ck / "config.json", "w"))
+    sd = {k: v.clone() for k, v in ckpt_model.state_dict().items() if "mamba_rev.in_proj" not in k and "mamba_rev.out_proj" not in k
+          and not k.startswith("lm_head")}
+    save_file(sd, str(ck / "model.safetensors"))
+    assert zs.main(["-input-vcf", vcf_in, "-input-fasta", str(fasta), "-output", vcf_out, "-model", str(ck), "-dtype", "float32",
+                    "-batchSize", "37"]) == 0
+    rows = [ln.rstrip("\n").split("\t") for ln in open(vcf_out) if not ln.startswith("#")]
+    assert len(rows) == len(res["pos"])
+    for k, f in enumerate(rows):
+        assert int(f[1]) == res["pos"][k] and f[3] == chr(res["ref"][k]) and f[4] == chr(res["alt"][k])
+        got = np.float32(f[7].split("plantCAD_zero_shot=")[1])
+        assert got == res["score"][k], (k, got, res["score"][k])
+
+
+def test_extract_embeddings_matches_reference_formula(cuda_device):
+    """`extract_embeddings` (reference src/train_XGBoost.py:96-114): hidden_states[-1][:, tokenIdx, :] -> fp32 ->
+    (fwd + rev[..., ::-1]) / 2, through the per-position tap (no [B, L, 2d] tensor)."""
+    from plantcaduceus_b200 import CharDNATokenizer
+    from plantcaduceus_b200.embeddings import extract_embeddings
+    from plantcaduceus_b200.modeling import CaduceusForMaskedLM
+    cfg = CaduceusConfig(d_model=128, n_layer=2)
+    sd = random_init_state_dict(cfg, seed=31)
+    tok = CharDNATokenizer()
+    rng = np.random.default_rng(2)
+    N, L, idx = 7, 512, 255
+    seqs = ["".join(rng.choice(list("ACGT"), size=L)) for _ in range(N)]
+    ids = torch.from_numpy(tok.encode_bytes(tok.windows_to_ascii(seqs, L)).astype(np.int64))
+    _, hs = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32, output_hidden_states=True)
+    e = hs[-1][:, idx, :].numpy()
+    want = (e[..., :cfg.d_model] + e[..., cfg.d_model:][..., ::-1]) / 2
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 3e-2)):
+        model = CaduceusForMaskedLM.from_pretrained(sd, config=cfg, torch_dtype=dtype).to(cuda_device)
+        got = extract_embeddings(model, tok, seqs, tokenIdx=idx, batch_size=3)
+        assert got.shape == (N, cfg.d_model) and got.dtype == np.float32
+        assert np.abs(got - want).max() <= tol * np.abs(want).max()
+        # the tap equals the materialised hidden state, bit for bit
+        full = model(input_ids=ids.to(cuda_device), output_hidden_states=True).hidden_states[-1][:, idx, :]
+        tap = model.hidden_at(ids.to(torch.uint8), torch.full((N, 1), idx, dtype=torch.int32))[:, 0]
+        assert torch.equal(full, tap)
+
+
+def test_unmasked_probs_long_context_matches_oracle(cuda_device):
+    """`_unmasked_probs` (reference src/zero-shot-eval.py:143-178) at the PlantCAD2 context length: [N, 8192, 4]
+    probabilities from the full-length head, against the oracle."""
+    from plantcaduceus_b200 import CharDNATokenizer
+    from plantcaduceus_b200 import zero_shot_eval as zse
+    from plantcaduceus_b200.modeling import CaduceusForMaskedLM
+    cfg = CaduceusConfig(d_model=128, n_layer=2)
+    sd = random_init_state_dict(cfg, seed=41)
+    tok = CharDNATokenizer()
+    rng = np.random.default_rng(8)
+    N, L = 2, 8192
+    seqs = ["".join(rng.choice(list("ACGT"), size=L)) for _ in range(N)]
+    model = CaduceusForMaskedLM.from_pretrained(sd, config=cfg, torch_dtype=torch.float32).to(cuda_device)
+    got = zse.unmasked_probs(model, tok, seqs, batch_size=1)
+    ids = torch.from_numpy(tok.encode_bytes(tok.windows_to_ascii(seqs, L)).astype(np.int64))
+    lg, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    want = torch.softmax(lg[..., 3:7].float(), dim=-1).numpy()
+    assert got.shape == (N, L, 4) and np.allclose(got, want, rtol=2e-4, atol=1e-6)

@@ -70,3 +70,92 @@ def test_score_gather_world_size_2_gloo(n):
         assert p.exitcode == 0
     results = dict(q.get(timeout=10) for _ in range(2))
     assert results == {0: True, 1: True}
+
+
+class _FakeEngine:
+    """CPU stand-in with the two device entry points genome_scan uses: windows by the host rule, scores = a function of
+    the window bytes (so a wrong chromosome, position or order shows)."""
+    device = torch.device("cpu")
+
+    def extract_windows_device(self, chrom_dev, pos0, token_idx=255, length=512):
+        from plantcaduceus_b200 import genome_io as gio
+        chrom = bytes(chrom_dev.numpy())
+        rows = [np.frombuffer(gio.extract_window(chrom, int(p), token_idx, length), dtype=np.uint8) for p in pos0.tolist()]
+        return torch.from_numpy(np.stack(rows).copy()) if rows else torch.zeros((0, length), dtype=torch.uint8)
+
+    def score_windows_device(self, windows, token_idx, out=None):
+        res = torch.from_numpy(_fake_score(windows.numpy()))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+
+def _genome_case():
+    rng = np.random.default_rng(5)
+    seqs = {f"chr{i}": bytes(rng.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8), size=700 + 300 * i)) for i in range(3)}
+    names = ["chr2", "chr0", "chr1"]          # order of first appearance in the VCF, not the FASTA's
+    cid = rng.integers(0, 2, 41).astype(np.int32)       # chr1 (id 2) carries no variant: never broadcast
+    pos = np.array([rng.integers(0, len(seqs[names[c]])) for c in cid], dtype=np.int64)
+    return names, seqs, cid, pos
+
+
+def _worker_genome(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from plantcaduceus_b200 import genome_io as gio
+        from plantcaduceus_b200.genome_scan import score_variants_sharded
+        from plantcaduceus_b200.sharding import scatter_rows
+        names, seqs, cid, pos = _genome_case()
+        args = (names, seqs, cid, pos) if rank == 0 else (None, None, None, None)     # only rank 0 has parsed anything
+        got = score_variants_sharded(_FakeEngine(), *args, batch_size=7, token_idx=20, length=64, device=torch.device("cpu"))
+        want = _fake_score(np.stack([np.frombuffer(gio.extract_window(seqs[names[c]], int(p), 20, 64), dtype=np.uint8)
+                                     for c, p in zip(cid, pos)]))
+        ok = np.array_equal(got, want)
+        rows = torch.arange(23 * 3, dtype=torch.uint8).reshape(23, 3) if rank == 0 else None
+        mine = scatter_rows(rows)
+        s, e = shard_range(23, rank, world)
+        ok = ok and torch.equal(mine, torch.arange(23 * 3, dtype=torch.uint8).reshape(23, 3)[s:e])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank0_parses_and_broadcasts_world_size_2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_genome, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    results = dict(q.get(timeout=10) for _ in range(2))
+    assert results == {0: True, 1: True}
+
+
+def test_score_variants_single_process_and_fasta_reader(tmp_path):
+    from plantcaduceus_b200 import genome_io as gio
+    from plantcaduceus_b200.genome_scan import score_variants_sharded
+    names, seqs, cid, pos = _genome_case()
+    got = score_variants_sharded(_FakeEngine(), names, seqs, cid, pos, batch_size=16, token_idx=20, length=64, device=torch.device("cpu"))
+    want = _fake_score(np.stack([np.frombuffer(gio.extract_window(seqs[names[c]], int(p), 20, 64), dtype=np.uint8)
+                                 for c, p in zip(cid, pos)]))
+    assert np.array_equal(got, want)
+    # vectorised FASTA reader: wrapped lines, CRLF, blank lines, description after the id, text before the first header
+    fa = tmp_path / "g.fa"
+    body = lambda s, w, nl: nl.join(s[i:i + w].decode() for i in range(0, len(s), w))
+    fa.write_bytes(("junk before any header\n>chr0 first record\n" + body(seqs["chr0"], 60, "\n") + "\n\n>chr1\tdesc\r\n"
+                    + body(seqs["chr1"], 50, "\r\n") + "\r\n>chr2\n" + body(seqs["chr2"], 80, "\n")).encode())
+    assert gio.read_fasta(str(fa)) == seqs
+    import gzip
+    with gzip.open(str(fa) + ".gz", "wb") as f:
+        f.write(fa.read_bytes())
+    assert gio.read_fasta(str(fa) + ".gz") == seqs
+    fa.write_bytes(b">a\nAC\n>a\nGT\n")
+    with pytest.raises(ValueError, match="duplicate"):
+        gio.read_fasta(str(fa))
