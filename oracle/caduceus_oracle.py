@@ -1,4 +1,4 @@
-"""CPU oracle for the PlantCaduceus (Caduceus / RC-equivariant BiMamba, Mamba-1) forward pass.
+"""CPU oracle for the PlantCaduceus (Caduceus / RC-equivariant BiMamba; Mamba-1, and Mamba-2 for PlantCAD2) forward pass.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``plantcaduceus_b200/`` may import this module; it is
 used by ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
@@ -83,20 +83,77 @@ def mamba_mixer(u, p: Dict[str, torch.Tensor]):
 
 
 # --------------------------------------------------------------------------------------------
+# Mamba-2 / SSD mixer  [EXT mamba_ssm/modules/mamba2.py: Mamba2.forward, non-fused branch
+#                       (use_mem_eff_path=False); mamba_ssm/ops/triton/ssd_combined.py:
+#                       mamba_chunk_scan_combined == the recurrence below (ssd_minimal / selective_state_update);
+#                       mamba_ssm/ops/triton/layernorm_gated.py: rmsnorm_fn(norm_before_gate=False)]
+# PlantCAD2 checkpoints (reference docs/PlantCAD2-overview.md:17-21, src/zero-shot-eval.py:54-72) use this mixer.
+# --------------------------------------------------------------------------------------------
+def ssd_scan_ref(x, dt, A, B, C, D, dt_bias):
+    """x: [b, L, H, P]; dt: [b, L, H] (raw); A, D, dt_bias: [H] fp32; B, C: [b, L, G, N].  Sequential state-space
+    recurrence with scalar decay per head: dt = softplus(dt + dt_bias); S <- exp(dt A) S + dt x (x) B; y = S C + D x.
+    fp32 state, output cast to x.dtype (the SSD kernels accumulate in fp32 and store the I/O dtype)."""
+    dtype_in = x.dtype
+    b, L, H, P = x.shape
+    G, N = B.shape[2], B.shape[3]
+    x = x.float()
+    dt = F.softplus(dt.float() + dt_bias.float()[None, None, :])
+    Bh = B.float().repeat_interleave(H // G, dim=2)          # [b, L, H, N]
+    Ch = C.float().repeat_interleave(H // G, dim=2)
+    S = torch.zeros((b, H, P, N), dtype=torch.float32)
+    ys = []
+    for t in range(L):
+        dA = torch.exp(dt[:, t] * A[None, :])                                   # [b, H]
+        dBx = (dt[:, t, :, None] * x[:, t])[..., None] * Bh[:, t, :, None, :]     # [b, H, P, N]
+        S = dA[:, :, None, None] * S + dBx
+        ys.append((S * Ch[:, t, :, None, :]).sum(-1))                           # [b, H, P]
+    y = torch.stack(ys, dim=1) + x * D.float()[None, None, :, None]
+    return y.to(dtype_in)
+
+
+def rmsnorm_gated(y, z, weight, eps):
+    """[EXT RMSNormGated(norm_before_gate=False, group_size=d_inner)]: fp32 y * silu(z), RMS over the whole row, * weight."""
+    xf = y.float() * F.silu(z.float())
+    rstd = torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return (xf * rstd * weight.float()).to(y.dtype)
+
+
+def mamba2_mixer(u, p: Dict[str, torch.Tensor], headdim: int = 64, ngroups: int = 1, eps: float = 1e-5):
+    """One direction of Mamba-2 on u [b, L, d].  in_proj rows are ordered z | x | B | C | dt."""
+    b, L, d = u.shape
+    E = p["norm.weight"].shape[0]
+    H = p["A_log"].shape[0]
+    CD = p["conv1d.weight"].shape[0]
+    N = (CD - E) // (2 * ngroups)
+    zxbcdt = F.linear(u, p["in_proj.weight"])                                  # [b, L, 2E + 2GN + H]
+    z, xBC, dt = torch.split(zxbcdt, [E, CD, H], dim=-1)
+    xc = F.conv1d(xBC.transpose(1, 2).float(), p["conv1d.weight"].float(), p["conv1d.bias"].float(),
+                  padding=p["conv1d.weight"].shape[-1] - 1, groups=CD)[..., :L]
+    xBC = F.silu(xc).transpose(1, 2).to(u.dtype)
+    x, Bm, Cm = torch.split(xBC, [E, ngroups * N, ngroups * N], dim=-1)
+    A = -torch.exp(p["A_log"].float())
+    y = ssd_scan_ref(x.reshape(b, L, H, headdim), dt, A, Bm.reshape(b, L, ngroups, N), Cm.reshape(b, L, ngroups, N),
+                     p["D"].float(), p["dt_bias"].float())
+    y = rmsnorm_gated(y.reshape(b, L, E), z, p["norm.weight"], eps)
+    return F.linear(y, p["out_proj.weight"])
+
+
+# --------------------------------------------------------------------------------------------
 # Caduceus wrappers  [EXT HF-hub modeling_caduceus.py / modeling_rcps.py]
 # --------------------------------------------------------------------------------------------
-def bimamba(u, p_fwd, p_rev):
+def bimamba(u, p_fwd, p_rev, mixer=None):
     """[EXT BiMambaWrapper.forward], strategy "add": fwd(u) + flip_L(rev(flip_L(u)))."""
-    out = mamba_mixer(u, p_fwd)
-    out_rev = mamba_mixer(u.flip(dims=(1,)), p_rev).flip(dims=(1,))
+    mixer = mixer or mamba_mixer
+    out = mixer(u, p_fwd)
+    out_rev = mixer(u.flip(dims=(1,)), p_rev).flip(dims=(1,))
     return out + out_rev
 
 
-def rcps_wrapper(x, p_fwd, p_rev):
+def rcps_wrapper(x, p_fwd, p_rev, mixer=None):
     """[EXT RCPSWrapper.forward]: same submodule on the fwd half and on flip_{L,D}(RC half)."""
     d = x.shape[-1] // 2
-    fwd_out = bimamba(x[..., :d], p_fwd, p_rev)
-    rc_out = bimamba(torch.flip(x[..., d:], dims=[-2, -1]), p_fwd, p_rev)
+    fwd_out = bimamba(x[..., :d], p_fwd, p_rev, mixer)
+    rc_out = bimamba(torch.flip(x[..., d:], dims=[-2, -1]), p_fwd, p_rev, mixer)
     return torch.cat([fwd_out, torch.flip(rc_out, dims=[-2, -1])], dim=-1)
 
 
@@ -142,14 +199,18 @@ def rcps_lm_head(x, weight, comp):
     return fwd + rc
 
 
-def _dir_params(sd, i, direction, dtype):
+_M1_NAMES = ("in_proj.weight", "conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight",
+             "dt_proj.bias", "A_log", "D", "out_proj.weight")
+_M2_NAMES = ("in_proj.weight", "conv1d.weight", "conv1d.bias", "dt_bias", "A_log", "D", "norm.weight", "out_proj.weight")
+
+
+def _dir_params(sd, i, direction, dtype, names=_M1_NAMES):
     pre = f"caduceus.backbone.layers.{i}.mixer.submodule.{direction}."
     out = {}
-    for name in ("in_proj.weight", "conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight",
-                 "dt_proj.bias", "A_log", "D", "out_proj.weight"):
+    for name in names:
         t = sd[pre + name]
-        # from_pretrained(torch_dtype=dtype) casts every parameter; Mamba reads A_log / D back with .float()
-        out[name] = t.to(dtype).float() if name in ("A_log", "D") else t.to(dtype)
+        # from_pretrained(torch_dtype=dtype) casts every parameter; Mamba reads A_log / D (/ dt_bias) back with .float()
+        out[name] = t.to(dtype).float() if name in ("A_log", "D", "dt_bias") else t.to(dtype)
     return out
 
 
@@ -167,13 +228,17 @@ def caduceus_forward(sd: Dict[str, torch.Tensor], cfg, input_ids: torch.Tensor,
     eps = cfg.norm_epsilon
     hidden = rcps_embedding(input_ids, emb, comp)
     residual = None
+    mamba2 = getattr(cfg, "is_mamba2", False)
+    names = _M2_NAMES if mamba2 else _M1_NAMES
+    mixer = (lambda u, p: mamba2_mixer(u, p, cfg.headdim, cfg.ngroups)) if mamba2 else mamba_mixer
     all_hidden = [] if output_hidden_states else None
     for i in range(cfg.n_layer):
         if output_hidden_states:
             all_hidden.append(hidden)
         w = sd[f"caduceus.backbone.layers.{i}.norm.weight"].to(dtype)
         hidden, residual = rcps_add_norm(hidden, residual, w, eps, cfg.residual_in_fp32, prenorm=True)
-        hidden = rcps_wrapper(hidden, _dir_params(sd, i, "mamba_fwd", dtype), _dir_params(sd, i, "mamba_rev", dtype))
+        hidden = rcps_wrapper(hidden, _dir_params(sd, i, "mamba_fwd", dtype, names), _dir_params(sd, i, "mamba_rev", dtype, names),
+                              mixer)
     w_f = sd["caduceus.backbone.norm_f.weight"].to(dtype)
     hidden = rcps_add_norm(hidden, residual, w_f, eps, cfg.residual_in_fp32, prenorm=False)
     if output_hidden_states:

@@ -83,6 +83,38 @@ class CaduceusConfig:
         r = self.ssm_cfg.get("dt_rank", "auto")
         return math.ceil(self.d_model / 16) if r == "auto" else int(r)
 
+    # Mamba-2 / SSD mixer (PlantCAD2, reference docs/PlantCAD2-overview.md:17-21).  mamba_ssm's block factory reads the
+    # layer type from ssm_cfg["layer"] ("Mamba1" default, "Mamba2"); the Mamba2 hyper-parameters keep its names.
+    @property
+    def mixer(self) -> str:
+        return str(self.ssm_cfg.get("layer", "Mamba1"))
+
+    @property
+    def is_mamba2(self) -> bool:
+        return self.mixer == "Mamba2"
+
+    @property
+    def headdim(self) -> int:
+        return int(self.ssm_cfg.get("headdim", 64))
+
+    @property
+    def ngroups(self) -> int:
+        return int(self.ssm_cfg.get("ngroups", 1))
+
+    @property
+    def nheads(self) -> int:
+        return self.d_inner // self.headdim
+
+    @property
+    def conv_dim(self) -> int:
+        """Channels that go through the depthwise conv: x | B | C (Mamba2.conv1d)."""
+        return self.d_inner + 2 * self.ngroups * self.d_state
+
+    @property
+    def d_in_proj(self) -> int:
+        """Mamba2.in_proj output width: z | x | B | C | dt."""
+        return 2 * self.d_inner + 2 * self.ngroups * self.d_state + self.nheads
+
     def validate_supported(self) -> None:
         """Raise ValueError for configurations the engine does not implement."""
         bad = []
@@ -96,7 +128,22 @@ class CaduceusConfig:
             bad.append("bidirectional_weight_tie=False")
         if not self.rms_norm:
             bad.append("rms_norm=False")
-        if self.d_state != 16:
+        if self.mixer not in ("Mamba1", "Mamba2"):
+            bad.append(f"ssm_cfg.layer={self.mixer!r}")
+        if self.is_mamba2:
+            # the SSD kernel is specialised for the PlantCAD2 shape: 64-wide heads, 64 states, one B/C group
+            if self.d_state != 64:
+                bad.append(f"d_state={self.d_state} (Mamba2 engine is specialised for 64)")
+            if self.headdim != 64:
+                bad.append(f"headdim={self.headdim} (Mamba2 engine is specialised for 64)")
+            if self.ngroups != 1:
+                bad.append(f"ngroups={self.ngroups} (Mamba2 engine is specialised for 1)")
+            if self.d_inner % (2 * self.headdim) != 0:
+                bad.append(f"nheads={self.nheads} must be even")
+            for key, want in (("rmsnorm", True), ("norm_before_gate", False), ("D_has_hdim", False)):
+                if self.ssm_cfg.get(key, want) != want:
+                    bad.append(f"ssm_cfg.{key}={self.ssm_cfg.get(key)!r}")
+        elif self.d_state != 16:
             bad.append(f"d_state={self.d_state} (engine is specialised for 16)")
         if self.d_conv != 4:
             bad.append(f"d_conv={self.d_conv} (engine is specialised for 4)")
@@ -109,7 +156,7 @@ class CaduceusConfig:
             bad.append(f"d_model={self.d_model} (engine needs a multiple of 128, <= 2048)")
         if self.expand != 2:
             bad.append(f"expand={self.expand} (engine is specialised for 2)")
-        if self.dt_rank <= 0 or self.dt_rank % 8 != 0:
+        if not self.is_mamba2 and (self.dt_rank <= 0 or self.dt_rank % 8 != 0):
             bad.append(f"dt_rank={self.dt_rank} (engine needs a multiple of 8)")
         if not self.fused_add_norm:
             bad.append("fused_add_norm=False (different module tree, key names and rounding order)")
@@ -141,15 +188,29 @@ PRESETS = {
     "PlantCaduceus_l28": dict(d_model=768, n_layer=28),
     "PlantCaduceus_l32": dict(d_model=1024, n_layer=32),
 }
+# PlantCAD2 (reference docs/PlantCAD2-overview.md:17-21; 8192-bp context).  The Mamba-2 hyper-parameters are not stated in
+# the reference; d_state 64 / headdim 64 / ngroups 1 / expand 2 with tied in/out projections are the values that reproduce
+# the published parameter counts 88 M / 311 M / 694 M (img/PlantCAD2-difference.jpg) to three digits (tests/test_oracle.py).
+_MAMBA2 = dict(layer="Mamba2", d_state=64, d_conv=4, expand=2, headdim=64, ngroups=1, conv_bias=True, bias=False, chunk_size=256)
+PRESETS.update({
+    "PlantCAD2-Small-l24-d0768": dict(d_model=768, n_layer=24, ssm_cfg=dict(_MAMBA2)),
+    "PlantCAD2-Medium-l48-d1024": dict(d_model=1024, n_layer=48, ssm_cfg=dict(_MAMBA2)),
+    "PlantCAD2-Large-l48-d1536": dict(d_model=1536, n_layer=48, ssm_cfg=dict(_MAMBA2)),
+})
+_ALIASES = {"cad2-small": "PlantCAD2-Small-l24-d0768", "cad2-medium": "PlantCAD2-Medium-l48-d1024",
+            "cad2-large": "PlantCAD2-Large-l48-d1536"}
 
 
 def preset(name: str, **overrides) -> CaduceusConfig:
     key = name.split("/")[-1]
+    key = _ALIASES.get(key, key)
     if key in PRESETS:
         kw = dict(PRESETS[key])
     elif "PlantCaduceus_" + key in PRESETS:
         kw = dict(PRESETS["PlantCaduceus_" + key])
     else:
         raise KeyError(f"unknown preset {name!r}; known: {sorted(PRESETS)}")
+    if "ssm_cfg" in kw:
+        kw["ssm_cfg"] = dict(kw["ssm_cfg"])
     kw.update(overrides)
     return CaduceusConfig(**kw)

@@ -39,6 +39,9 @@ HEAD_KEY = "lm_head.lm_head.weight"
 NORM_F_KEY = PREFIX + "norm_f.weight"
 DIRS = ("mamba_fwd", "mamba_rev")
 PER_DIR = ("conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight", "dt_proj.bias", "A_log", "D")
+# Mamba-2 ([EXT] mamba_ssm.modules.mamba2.Mamba2): in_proj [2E + 2GN + H, d] and out_proj [d, E] tied between the directions;
+# per direction conv1d.weight [E + 2GN, 1, 4], conv1d.bias [E + 2GN], dt_bias [H], A_log [H], D [H], norm.weight [E]
+PER_DIR_M2 = ("conv1d.weight", "conv1d.bias", "dt_bias", "A_log", "D", "norm.weight")
 SHARED = ("in_proj.weight", "out_proj.weight")
 
 
@@ -66,7 +69,23 @@ def random_init_state_dict(cfg: CaduceusConfig, seed: int = 0,
     emb = normal((V, d), 0.02)
     sd[EMB_KEY] = emb
     sd[HEAD_KEY] = emb  # tied (225.36 M parameter count)
-    for i in range(cfg.n_layer):
+    if cfg.is_mamba2:
+        H, CD, DIP = cfg.nheads, cfg.conv_dim, cfg.d_in_proj
+        for i in range(cfg.n_layer):
+            w_in = uniform((DIP, d), 1.0 / math.sqrt(d))
+            w_out = uniform((d, E), 1.0 / math.sqrt(E)) / math.sqrt(2.0 * cfg.n_layer)
+            for direction in DIRS:
+                sd[layer_key(i, direction, "in_proj.weight")] = w_in
+                sd[layer_key(i, direction, "out_proj.weight")] = w_out
+                sd[layer_key(i, direction, "conv1d.weight")] = uniform((CD, 1, K), 1.0 / math.sqrt(K))
+                sd[layer_key(i, direction, "conv1d.bias")] = uniform((CD,), 1.0 / math.sqrt(K))
+                dt = torch.exp(torch.rand((H,), generator=g) * (math.log(0.1) - math.log(1e-3)) + math.log(1e-3)).clamp(min=1e-4)
+                sd[layer_key(i, direction, "dt_bias")] = dt + torch.log(-torch.expm1(-dt))
+                sd[layer_key(i, direction, "A_log")] = torch.log(1.0 + 15.0 * torch.rand((H,), generator=g))   # A in (1, 16)
+                sd[layer_key(i, direction, "D")] = 1.0 + normal((H,), 0.1)
+                sd[layer_key(i, direction, "norm.weight")] = 1.0 + normal((E,), 0.1)
+            sd[norm_key(i)] = 1.0 + normal((d,), 0.1)
+    for i in range(0 if cfg.is_mamba2 else cfg.n_layer):
         w_in = uniform((2 * E, d), 1.0 / math.sqrt(d))
         w_out = uniform((d, E), 1.0 / math.sqrt(E)) / math.sqrt(2.0 * cfg.n_layer)
         for direction in DIRS:
