@@ -1,7 +1,7 @@
 /*
  * pcad.h -- C ABI of libpcad.so, the B200 (sm_100a) engine for the PlantCaduceus
- * (Caduceus / reverse-complement-equivariant BiMamba, Mamba-1) masked-LM forward pass and
- * its zero-shot variant-scoring path.
+ * (Caduceus / reverse-complement-equivariant BiMamba; Mamba-1 mixer for PlantCAD, Mamba-2 / SSD mixer for PlantCAD2)
+ * masked-LM forward pass and its zero-shot variant-scoring path.
  *
  * The reference has no C/FFI boundary of its own: the boundary is the Hugging Face Python object
  * returned by AutoModelForMaskedLM.from_pretrained(..., trust_remote_code=True)
@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PCAD_ABI_VERSION 1
+#define PCAD_ABI_VERSION 2
 
 typedef enum {
   PCAD_OK = 0,
@@ -39,6 +39,9 @@ typedef enum {
 } pcad_status;
 
 typedef enum { PCAD_BF16 = 0, PCAD_F32 = 1, PCAD_F16 = 2 } pcad_dtype;
+/* ssm_cfg["layer"] of the checkpoint's config: "Mamba1" (PlantCaduceus_l20..l32) or "Mamba2" (PlantCAD2,
+ * reference docs/PlantCAD2-overview.md:17-21, src/zero-shot-eval.py:54-72). */
+typedef enum { PCAD_MIXER_MAMBA1 = 0, PCAD_MIXER_MAMBA2 = 1 } pcad_mixer;
 
 /* Mirrors the keys of the checkpoint's config.json that the forward pass reads
  * (CaduceusConfig).  complement_map[i] is the token id of the complement
@@ -47,14 +50,17 @@ typedef struct {
   int32_t d_model;
   int32_t n_layer;
   int32_t vocab_size;        /* padded to a multiple of 8 (caduceus.py:124-125); engine requires 8 */
-  int32_t d_state;           /* 16 */
+  int32_t d_state;           /* 16 (Mamba-1) / 64 (Mamba-2) */
   int32_t d_conv;            /* 4  */
   int32_t expand;            /* 2  */
-  int32_t dt_rank;           /* ceil(d_model / 16) */
+  int32_t dt_rank;           /* ceil(d_model / 16); ignored for Mamba-2 */
   float   norm_eps;
   int32_t residual_in_fp32;
   int32_t dtype;             /* pcad_dtype of activations and GEMM operands: PCAD_BF16 or PCAD_F32 */
   int32_t complement_map[16];
+  int32_t mixer;             /* pcad_mixer */
+  int32_t headdim;           /* Mamba-2: 64 */
+  int32_t ngroups;           /* Mamba-2: 1 */
 } pcad_config;
 
 typedef struct pcad_handle pcad_handle;
@@ -137,7 +143,7 @@ int pcad_workspace_bytes(pcad_handle* h, int B, int L, size_t* out);
  * accumulated milliseconds and launch counts since the last pcad_set_profiling(h, 1). */
 typedef enum {
   PCAD_ST_EMBED = 0, PCAD_ST_NORM, PCAD_ST_IN_PROJ, PCAD_ST_CONV, PCAD_ST_X_PROJ, PCAD_ST_DT_PROJ,
-  PCAD_ST_SCAN, PCAD_ST_OUT_PROJ, PCAD_ST_HEAD, PCAD_ST_MISC, PCAD_ST_COUNT
+  PCAD_ST_SCAN, PCAD_ST_OUT_PROJ, PCAD_ST_HEAD, PCAD_ST_MISC, PCAD_ST_GNORM /* Mamba-2 gated norms + add */, PCAD_ST_COUNT
 } pcad_stage;
 int pcad_set_profiling(pcad_handle* h, int enabled);
 int pcad_get_profile(pcad_handle* h, float ms[PCAD_ST_COUNT], int64_t launches[PCAD_ST_COUNT]);
@@ -154,30 +160,18 @@ int64_t pcad_launch_count(const pcad_handle* h);
 int pcad_op_linear(const void* A, const void* W, void* C, int64_t M, int N, int K,
                    int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream);
 
-/* C[M,N] = softplus(A W^T + bias[N]) (identity above 20), bf16 only: Mamba.dt_proj with the scan's
- * delta_bias / delta_softplus step [selective_scan_fn(..., delta_bias, delta_softplus=True)] applied in the GEMM
- * epilogue.  The result feeds pcad_op_biscan with delta_final = 1. */
-int pcad_op_linear_softplus(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
-                            int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream);
-
 /* The block's fused residual add + RMSNorm [mamba_ssm rms_norm_fn(prenorm=True)] folded into the two GEMMs around
  * it (bf16 only; what the bf16 forward runs when residual_in_fp32 = 0):
  *   pcad_op_linear_residual:  resid_out = A W^T + resid_in  (fp32 sum, stored bf16; resid_out may alias resid_in),
  *                             sumsq_out[row][p] = sum over column tile p of (fp32 sum)^2; float [M, pcad_op_sumsq_parts(N)],
  *                             every slot is written with a plain store (no atomics: results are deterministic)
  *   pcad_op_linear_rowscale:  C = (A W^T) * rsqrt(sum_p sumsq_in[row][p] / K + eps)   -- RMSNorm of A's rows applied
- *                             after the GEMM; the norm weight must be pre-multiplied into W's columns by the caller.
- *   pcad_op_linear_rowscale_silu: the same, and columns >= silu_from (a multiple of 64) are stored as SiLU(C): in_proj
- *                             with the selective scan's gate [selective_scan_fn(..., z): out = y * silu(z)] evaluated in
- *                             the GEMM epilogue.  Feeds pcad_op_biscan with bit 1 of delta_final set. */
+ *                             after the GEMM; the norm weight must be pre-multiplied into W's columns by the caller. */
 int pcad_op_sumsq_parts(int N);
 int pcad_op_linear_residual(const void* A, const void* W, const void* resid_in, void* resid_out, float* sumsq_out,
                             int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ld_res, int dtype, void* stream);
 int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in, int sumsq_parts, float eps, void* C,
                             int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream);
-int pcad_op_linear_rowscale_silu(const void* A, const void* W, const float* sumsq_in, int sumsq_parts, float eps,
-                                 int silu_from, void* C, int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc,
-                                 int dtype, void* stream);
 
 /* Fused residual add + RMSNorm [mamba_ssm rms_norm_fn, prenorm=True]:
  * res_out = x + res_in (res_in may be NULL); y = res_out * rsqrt(mean(res_out^2) + eps) * w.
@@ -194,43 +188,46 @@ int pcad_op_conv_silu(const void* x, int64_t ldx, const float* w_f, const float*
                       const float* w_r, const float* b_r, void* out_f, void* out_r,
                       int S, int L, int E, int dtype, void* stream);
 
-/* pcad_op_conv_silu and both directions' x_proj in one kernel (bf16 only; needs L % 128 == 0, E % 64 == 0 and
- * RP in {64, 80, 96}): out_f / out_r as pcad_op_conv_silu; dbc_f = out_f wx_f^T, dbc_r = out_r wx_r^T with wx_*: [RP, E]
- * bf16 (rows beyond dt_rank + 32 zero) and dbc_*: [S*L, RP].  The conv output goes to global memory for the scan and,
- * from the same registers, into the shared-memory A operand of the tcgen05 GEMM, so x_proj re-reads nothing. */
-int pcad_op_conv_xproj(const void* x, int64_t ldx, const float* w_f, const float* b_f, const float* w_r, const float* b_r,
-                       void* out_f, void* out_r, const void* wx_f, const void* wx_r, void* dbc_f, void* dbc_r,
-                       int S, int L, int E, int RP, int dtype, void* stream);
-
 /* Bidirectional selective scan with softplus(delta + bias), D skip and SiLU(z) gate
  * [selective_scan_fn(..., delta_softplus=True)], both directions summed before the gate
  * [BiMambaWrapper, strategy "add"]:
  *   u_*, delta_*: [S*L, E];  bc_*: [S*L, ldbc] with B at columns [bc_off, bc_off+16) and C at
  *   [bc_off+16, bc_off+32);  z: [S*L, E] with row pitch ldz;  A_*: float [E, 16] (= -exp(A_log));
- *   D_*, dt_bias_*: float [E];  y: [S*L, E].
- *   delta_final = 0: delta_* are raw dt_proj outputs, the kernel applies softplus(delta + dt_bias) itself (the
- *   reference's order of operations);  delta_final = 1: delta_* already hold softplus(dt_proj + dt_bias)
- *   (pcad_op_linear_softplus) and dt_bias_* are ignored.
- *   delta_final is a bit set: bit 0 as above; bit 1 (bf16 only): z already holds SiLU(z)
- *   (pcad_op_linear_rowscale_silu), the kernel multiplies by it as is. */
+ *   D_*, dt_bias_*: float [E];  y: [S*L, E].  delta_* are raw dt_proj outputs: the kernel applies
+ *   softplus(delta + dt_bias) itself (the reference's order of operations). */
 int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f,
                    const void* u_r, const void* delta_r, const void* bc_r,
                    int64_t ldbc, int bc_off, const void* z, int64_t ldz,
                    const float* A_f, const float* D_f, const float* dt_bias_f,
                    const float* A_r, const float* D_r, const float* dt_bias_r,
-                   void* y, int S, int L, int E, int delta_final, int dtype, void* stream);
+                   void* y, int S, int L, int E, int dtype, void* stream);
 
 /* The same with Mamba.dt_proj [F.linear(dt, dt_proj.weight)] computed inside the scan kernel (bf16 only): dbc_* are the
  * x_proj outputs [S*L, ldbc] (dt in columns [0, R), B at [bc_off, bc_off+16), C at [bc_off+16, bc_off+32); ldbc >= 64),
  * wdt_* the dt_proj weights re-laid by pcad_op_prep_dt_weight ([E, R] with row pitch ldw -> [E, 64], R <= 64).  Delta is
- * rounded to bf16 where the GEMM would have rounded it, so the result matches pcad_op_linear + pcad_op_biscan.
- * flags: bit 1 as pcad_op_biscan's delta_final bit 1 (z already gated); bit 0 must be clear. */
+ * rounded to bf16 where the GEMM would have rounded it, so the result matches pcad_op_linear + pcad_op_biscan. */
 int pcad_op_prep_dt_weight(const void* W, int64_t ldw, void* out, int E, int R, void* stream);
 int pcad_op_biscan_dt(const void* u_f, const void* dbc_f, const void* u_r, const void* dbc_r, int64_t ldbc, int bc_off,
                       const void* wdt_f, const void* wdt_r, const void* z, int64_t ldz,
                       const float* A_f, const float* D_f, const float* dt_bias_f,
                       const float* A_r, const float* D_r, const float* dt_bias_r,
-                      void* y, int S, int L, int E, int flags, void* stream);
+                      void* y, int S, int L, int E, void* stream);
+
+/* Mamba-2 / SSD selective scan [mamba_chunk_scan_combined(x, dt, A, B, C, D=D, z=None, dt_bias, dt_softplus=True)] for
+ * both time directions (direction by index math): xbc_f / xbc_r are the two directions' conv + SiLU outputs
+ * [S*L, ld_xbc] with x at columns [0, 64 H), B at [64 H, 64 H + 64), C at [64 H + 64, 64 H + 128) (64-wide heads, 64
+ * states, one B/C group); dt_raw [S*L, ld_dt] holds the raw dt, one column per head (shared by the directions: in_proj is
+ * tied); A_* (= -exp(A_log)), D_*, dt_bias_*: float [H]; y_f / y_r: [S*L, 64 H], y_r written at the original positions.
+ * bf16: chunked SSD on tcgen05 (H even), or the sequential recurrence when sequential != 0; f32: sequential recurrence. */
+int pcad_op_ssd_scan(const void* xbc_f, const void* xbc_r, int64_t ld_xbc, const void* dt_raw, int64_t ld_dt,
+                     const float* A_f, const float* D_f, const float* dt_bias_f,
+                     const float* A_r, const float* D_r, const float* dt_bias_r,
+                     void* y_f, void* y_r, int S, int L, int H, int dtype, int sequential, void* stream);
+
+/* Mamba2's RMSNormGated(norm_before_gate=False, one group) of each direction followed by BiMambaWrapper's "add":
+ * out = rms(y_f * silu(z)) * w_f + rms(y_r * silu(z)) * w_r, rows of E channels; z has row pitch ldz. */
+int pcad_op_gated_norm_sum(const void* y_f, const void* y_r, const void* z, int64_t ldz, const float* w_f,
+                           const float* w_r, void* out, int64_t rows, int E, float eps, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,14 +14,17 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libpcad.so"
 
 PCAD_BF16, PCAD_F32, PCAD_F16 = 0, 1, 2
-STAGES = ("embed", "norm", "in_proj", "conv", "x_proj", "dt_proj", "scan", "out_proj", "head", "misc")
+STAGES = ("embed", "norm", "in_proj", "conv", "x_proj", "dt_proj", "scan", "out_proj", "head", "misc", "gnorm")
+PCAD_MIXER_MAMBA1, PCAD_MIXER_MAMBA2 = 0, 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "pcad_abi_version", "pcad_create", "pcad_destroy", "pcad_last_error", "pcad_set_weight", "pcad_finalize",
     "pcad_set_tokenizer", "pcad_take_id_error", "pcad_hidden_at", "pcad_forward", "pcad_score_masked", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
     "pcad_workspace_bytes", "pcad_set_profiling", "pcad_get_profile", "pcad_launch_count",
-    "pcad_op_linear", "pcad_op_linear_softplus", "pcad_op_linear_residual", "pcad_op_linear_rowscale", "pcad_op_linear_rowscale_silu", "pcad_op_sumsq_parts",
-    "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_conv_xproj", "pcad_op_biscan", "pcad_op_biscan_dt", "pcad_op_prep_dt_weight",
+    "pcad_op_linear", "pcad_op_linear_residual", "pcad_op_linear_rowscale", "pcad_op_sumsq_parts",
+    "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_biscan", "pcad_op_biscan_dt", "pcad_op_prep_dt_weight",
+    "pcad_op_ssd_scan", "pcad_op_gated_norm_sum",
 )
 
 
@@ -30,6 +33,7 @@ class PcadConfig(C.Structure):
         ("d_model", C.c_int32), ("n_layer", C.c_int32), ("vocab_size", C.c_int32), ("d_state", C.c_int32),
         ("d_conv", C.c_int32), ("expand", C.c_int32), ("dt_rank", C.c_int32), ("norm_eps", C.c_float),
         ("residual_in_fp32", C.c_int32), ("dtype", C.c_int32), ("complement_map", C.c_int32 * 16),
+        ("mixer", C.c_int32), ("headdim", C.c_int32), ("ngroups", C.c_int32),
     ]
 
 
@@ -75,20 +79,21 @@ def load() -> C.CDLL:
     lib.pcad_launch_count.argtypes = [vp]
     lib.pcad_launch_count.restype = i64
     lib.pcad_op_linear.argtypes = [vp, vp, vp, i64, i32, i32, i64, i64, i64, i32, vp]
-    lib.pcad_op_linear_softplus.argtypes = [vp, vp, vp, vp, i64, i32, i32, i64, i64, i64, i32, vp]
     lib.pcad_op_linear_residual.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i64, i64, i64, i32, vp]
     lib.pcad_op_linear_rowscale.argtypes = [vp, vp, vp, i32, C.c_float, vp, i64, i32, i32, i64, i64, i64, i32, vp]
-    lib.pcad_op_linear_rowscale_silu.argtypes = [vp, vp, vp, i32, C.c_float, i32, vp, i64, i32, i32, i64, i64, i64, i32, vp]
     lib.pcad_op_sumsq_parts.argtypes = [i32]
     lib.pcad_op_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, i32, i32, vp]
     lib.pcad_op_conv_silu.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
-    lib.pcad_op_conv_xproj.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.pcad_op_prep_dt_weight.argtypes = [vp, i64, vp, i32, i32, vp]
-    lib.pcad_op_biscan_dt.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.pcad_op_biscan_dt.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.pcad_op_biscan.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp,
-                                   i32, i32, i32, i32, i32, vp]
+                                   i32, i32, i32, i32, vp]
+    lib.pcad_op_ssd_scan.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.pcad_op_gated_norm_sum.argtypes = [vp, vp, vp, i64, vp, vp, vp, i64, i32, C.c_float, i32, vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here means header and library disagree
+    if lib.pcad_abi_version() != ABI_VERSION:
+        raise PcadError(f"{path} has ABI version {lib.pcad_abi_version()}, this package needs {ABI_VERSION}: rebuild the extension")
     _lib = lib
     return lib
 

@@ -19,10 +19,7 @@ namespace pcad {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 
-// EW = number of epilogue warps: 4 (one per TMEM lane quarter), or 8 (two per quarter, alternating 64-column
-// chunks) for epilogues that do real math per element (softplus) -- with one warp per scheduler that math is
-// latency-bound.  The EW = 8 configuration keeps only 2 ring stages (it is used with K <= 64, one k-block per tile)
-// so that the 8 x 2 staging slabs fit.
+// EW = number of epilogue warps: 4 (one per TMEM lane quarter).
 // CG = CTAs per tile: 1, or 2 = a CTA pair (cluster of two on one TPC) computing a 256 x BN tile with
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, so a stage is 32 KB
 // instead of 48 KB (6 stages instead of 4) and B crosses shared memory once per 256 output rows.
@@ -45,10 +42,7 @@ struct GemmCfg {
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kSlot + kEpiBytes + kBarBytes;
 };
 
-// Epilogues: kEpiPlain stores the accumulator; kEpiSoftplus stores softplus(acc + bias[col]) (identity above 20),
-// which is dt_proj with the selective scan's delta_softplus / delta_bias step moved up into the GEMM
-// ([EXT] selective_scan_fn(..., delta_bias, delta_softplus=True)): the scan is bound by the MUFU pipe, this
-// write-bound GEMM has it idle.
+// Epilogues: kEpiPlain stores the accumulator.
 //
 // kEpiResidual / kEpiRowScale fold the block's fused residual-add RMSNorm ([EXT] rms_norm_fn(prenorm=True)) into the
 // two GEMMs around it, so the bf16 forward has no norm kernel between layers:
@@ -58,13 +52,9 @@ struct GemmCfg {
 //                            forward is deterministic and the two strands stay bit-identical;
 //   in_proj,  kEpiRowScale:  C = acc * rsqrt(sum_parts sumsq[row][.] / K + eps), with the norm weight pre-multiplied
 //                            into the columns of W at load time: (r * rstd * w) W^T == rstd * (r (W diag(w))^T).
-//                            Columns >= silu_from (in_proj's z half) are stored as SiLU(C): the selective scan's gate
-//                            [selective_scan_fn(..., z)] computed where the MUFU pipe is idle (this GEMM is bound by
-//                            the tensor pipe, the scan by MUFU); the scan then only multiplies (ZGATED).
-enum { kEpiPlain = 0, kEpiSoftplus = 1, kEpiResidual = 2, kEpiRowScale = 3 };
+enum { kEpiPlain = 0, kEpiResidual = 2, kEpiRowScale = 3 };
 
 struct EpiParams {
-  const float* bias = nullptr;        // kEpiSoftplus: [N]
   const bf16* resid = nullptr;        // kEpiResidual: [M, N] with row pitch ld_res (may alias C)
   long long ld_res = 0;
   float* sumsq_out = nullptr;         // kEpiResidual: [M, sumsq_parts]; slot = column-tile index (every slot is written)
@@ -72,7 +62,6 @@ struct EpiParams {
   int sumsq_parts = 1;
   float inv_k = 0.f;                  // kEpiRowScale: 1 / (row length the sum of squares was taken over)
   float eps = 0.f;
-  int silu_from = 0x7fffffff;         // kEpiRowScale: columns >= silu_from (a multiple of 64) are stored as SiLU(value)
 };
 
 template <int BN, int EPI, int EW, int CG>
@@ -254,25 +243,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             r0[k] = __float_as_uint(__uint_as_float(r0[k]) * row_scale);
             r1[k] = __float_as_uint(__uint_as_float(r1[k]) * row_scale);
           }
-          if (n0 + c0 >= ep.silu_from) {   // warp-uniform: this 64-column chunk belongs to the gate half
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              r0[k] = __float_as_uint(silu<false>(__uint_as_float(r0[k])));
-              r1[k] = __float_as_uint(silu<false>(__uint_as_float(r1[k])));
-            }
-          }
-        }
-        if constexpr (EPI == kEpiSoftplus) {
-#pragma unroll
-          for (int g = 0; g < 16; ++g) {
-            const int col = n0 + c0 + g * 4;
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col + 4 <= N) b4 = *reinterpret_cast<const float4*>(ep.bias + col);   // N % 4 == 0 is checked by the host
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-            uint32_t* r = (g < 8) ? (r0 + g * 4) : (r1 + (g - 8) * 4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) r[k] = __float_as_uint(softplus<false>(__uint_as_float(r[k]) + bb[k]));
-          }
         }
         // row `lane` of the slab: 8 chunks of 16 bytes, chunk j stored at (j ^ (lane & 7)) -- the 128B swizzle
         uint8_t* row = dst + lane * 128;
@@ -393,10 +363,6 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
     *why = "gemm: pointers must be 16-byte aligned and row pitches multiples of 8 elements";
     return cudaErrorInvalidValue;
   }
-  if (epi == kEpiSoftplus && (!ep.bias || (N % 4) || (reinterpret_cast<uintptr_t>(ep.bias) & 15))) {
-    *why = "gemm: the softplus epilogue needs a 16-byte aligned bias and N % 4 == 0";
-    return cudaErrorInvalidValue;
-  }
   if (epi == kEpiResidual && (!ep.resid || !ep.sumsq_out || (N % 8) || (ep.ld_res % 8) ||
                               (reinterpret_cast<uintptr_t>(ep.resid) & 15))) {
     *why = "gemm: the residual epilogue needs resid (16-byte aligned, pitch % 8 == 0), sumsq_out and N % 8 == 0";
@@ -406,12 +372,12 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
     *why = "gemm: sumsq_parts must equal gemm_sumsq_parts(N)";
     return cudaErrorInvalidValue;
   }
-  if (epi == kEpiRowScale && (!ep.sumsq_in || (ep.silu_from != 0x7fffffff && (ep.silu_from % 64) != 0))) {
-    *why = "gemm: the row-scale epilogue needs sumsq_in (and silu_from a multiple of 64)";
+  if (epi == kEpiRowScale && !ep.sumsq_in) {
+    *why = "gemm: the row-scale epilogue needs sumsq_in";
     return cudaErrorInvalidValue;
   }
   const int BN = pick_bn(N);
-  const bool pair = cta_pair && BN == 256 && (N % 256) == 0 && K >= 256 && epi != kEpiSoftplus && num_sms >= 2;
+  const bool pair = cta_pair && BN == 256 && (N % 256) == 0 && K >= 256 && num_sms >= 2;
   CUtensorMap ta, tb, tc;
   if (!make_tmap_bf16(&ta, A, M, K, lda, kGemmBM) || !make_tmap_bf16(&tb, W, N, K, ldw, pair ? BN / 2 : BN) ||
       !make_tmap_bf16(&tc, C, M, N, ldc, 32)) {
@@ -427,7 +393,6 @@ inline cudaError_t gemm_bf16_tcgen05(const bf16* A, const bf16* W, bf16* C, long
   }
 #define PCAD_GEMM_EPI(BNV)                                                                                  \
   switch (epi) {                                                                                            \
-    case kEpiSoftplus: return launch_gemm_bn<BNV, kEpiSoftplus, 8>(ta, tb, tc, M, N, K, ep, num_sms, stream); \
     case kEpiResidual: return launch_gemm_bn<BNV, kEpiResidual>(ta, tb, tc, M, N, K, ep, num_sms, stream);  \
     case kEpiRowScale: return launch_gemm_bn<BNV, kEpiRowScale>(ta, tb, tc, M, N, K, ep, num_sms, stream);  \
     default: return launch_gemm_bn<BNV, kEpiPlain>(ta, tb, tc, M, N, K, ep, num_sms, stream);               \

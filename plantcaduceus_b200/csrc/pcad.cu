@@ -15,8 +15,8 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tcgen05.cuh"
-#include "conv_xproj.cuh"
 #include "scan.cuh"
+#include "ssd.cuh"
 
 using namespace pcad;
 
@@ -33,7 +33,8 @@ struct DirWeights {
   float* dt_bias = nullptr;  // [E]
   float* A = nullptr;        // [E, N] = -exp(A_log)
   float* D = nullptr;        // [E]
-  bool has[7] = {false, false, false, false, false, false, false};
+  float* gnorm_w = nullptr;  // Mamba-2: [E] weight of the mixer's gated RMSNorm (dt_bias, A, D are [H] there)
+  bool has[8] = {false, false, false, false, false, false, false, false};
 };
 
 struct LayerWeights {
@@ -71,11 +72,11 @@ struct pcad_handle {
   int device = 0;
   int num_sms = 148;
   int d = 0, E = 0, N = 16, R = 0, RP = 0, V = 8;
+  bool m2 = false;                     // Mamba-2 / SSD mixer (PlantCAD2)
+  bool ssd_seq = false;                // Mamba-2 bf16: run the sequential-recurrence kernel instead of the tcgen05 SSD (A/B switch)
+  int H = 0, CD = 0, DIP = 0, DIPP = 0;   // Mamba-2: heads, conv channels (x|B|C), in_proj width (z|x|B|C|dt) and its padded pitch
   bool f32 = false;
   bool fuse_dt = false;                // bf16: dt_proj computed inside the scan (mma.sync), no dt_proj launches, no delta in HBM
-  bool gate_in_gemm = false;           // bf16 + fused norm: SiLU(z) in in_proj's epilogue, the scan only multiplies (ZGATED)
-  bool dt_softplus_epilogue = false;   // bf16: softplus(dt_proj + bias) in the GEMM epilogue, scan takes delta as is
-  bool fuse_conv_xproj = false;   // bf16: conv + SiLU + both x_proj GEMMs in one kernel (L % 128 == 0)
   bool fuse_norm = false;   // bf16 activations + bf16 residual: add+RMSNorm folded into the out_proj / in_proj epilogues
   size_t act_size = 2;
   bool finalized = false;
@@ -304,23 +305,10 @@ int op_conv(pcad_handle* h, const void* x, long long ldx, const float* w_f, cons
   return PCAD_OK;
 }
 
-int op_conv_xproj(pcad_handle* h, const void* x, long long ldx, const float* w_f, const float* b_f, const float* w_r,
-                  const float* b_r, void* xc_f, void* xc_r, const void* wx_f, const void* wx_r, void* dbc_f, void* dbc_r,
-                  int S, int L, int E, int RP, int num_sms, cudaStream_t st) {
-  if (S <= 0 || L <= 0) return PCAD_OK;
-  const char* why = nullptr;
-  cudaError_t e = conv_xproj_bf16(static_cast<const bf16*>(x), ldx, w_f, b_f, w_r, b_r, static_cast<bf16*>(xc_f),
-                                  static_cast<bf16*>(xc_r), static_cast<const bf16*>(wx_f), static_cast<const bf16*>(wx_r),
-                                  static_cast<bf16*>(dbc_f), static_cast<bf16*>(dbc_r), static_cast<long long>(S) * L, L, E, RP,
-                                  num_sms, st, &why);
-  if (e != cudaSuccess) return fail(h, why ? PCAD_ERR_INVALID : PCAD_ERR_CUDA, "%s", why ? why : cudaGetErrorString(e));
-  return PCAD_OK;
-}
-
 int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* bc_f, const void* u_r,
               const void* delta_r, const void* bc_r, long long ldbc, int bc_off, const void* z, long long ldz,
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
-              const float* bias_r, void* y, int S, int L, int E, bool f32, bool delta_final, bool z_gated, cudaStream_t st,
+              const float* bias_r, void* y, int S, int L, int E, bool f32, cudaStream_t st,
               const void* wdt_f = nullptr, const void* wdt_r = nullptr) {
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
@@ -332,26 +320,16 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
   static_cast<const TT*>(u_f), static_cast<const TT*>(delta_f), static_cast<const TT*>(bc_f), static_cast<const TT*>(u_r), \
       static_cast<const TT*>(delta_r), static_cast<const TT*>(bc_r), ldbc, bc_off, static_cast<const TT*>(z), ldz, A_f, D_f, \
       bias_f, A_r, D_r, bias_r, static_cast<TT*>(y), S, L, E, st
-  if (f32 && z_gated) return fail(h, PCAD_ERR_INVALID, "biscan: a pre-gated z is a bf16-path feature");
   const bool fused_dt = wdt_f != nullptr || wdt_r != nullptr;
   if (fused_dt) {   // delta_* are the x_proj outputs, dt_proj runs inside the kernel
-    if (f32 || delta_final || !wdt_f || !wdt_r || ldbc < kScanDtK)
-      return fail(h, PCAD_ERR_INVALID, "biscan: the in-kernel dt_proj needs bf16, raw delta, both weights and ldbc >= 64");
-    cudaError_t e2;
-#define PCAD_SCAN_ARGS_DT                                                                                               \
-  static_cast<const bf16*>(u_f), static_cast<const bf16*>(delta_f), static_cast<const bf16*>(bc_f),                       \
-      static_cast<const bf16*>(u_r), static_cast<const bf16*>(delta_r), static_cast<const bf16*>(bc_r), ldbc, bc_off,       \
-      static_cast<const bf16*>(z), ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, static_cast<bf16*>(y), S, L, E, st,             \
-      static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r)
-    if (z_gated) e2 = launch_biscan<bf16, false, false, true, true>(PCAD_SCAN_ARGS_DT);
-    else e2 = launch_biscan<bf16, false, false, false, true>(PCAD_SCAN_ARGS_DT);
-#undef PCAD_SCAN_ARGS_DT
-    CUDA_TRY(h, e2);
-    return PCAD_OK;
+    if (f32 || !wdt_f || !wdt_r || ldbc < kScanDtK)
+      return fail(h, PCAD_ERR_INVALID, "biscan: the in-kernel dt_proj needs bf16, both weights and ldbc >= 64");
+    e = launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16), static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r));
+  } else if (f32) {
+    e = launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float));
+  } else {
+    e = launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16));
   }
-  if (f32) e = delta_final ? launch_biscan<float, true, true>(PCAD_SCAN_ARGS(float)) : launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float));
-  else if (z_gated) e = delta_final ? launch_biscan<bf16, false, true, true>(PCAD_SCAN_ARGS(bf16)) : launch_biscan<bf16, false, false, true>(PCAD_SCAN_ARGS(bf16));
-  else e = delta_final ? launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16)) : launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16));
 #undef PCAD_SCAN_ARGS
   CUDA_TRY(h, e);
   return PCAD_OK;
@@ -370,9 +348,11 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
   const size_t o_hid = take(T * h->d * a);
   const size_t o_res = take(T * h->d * rs);
   const size_t o_nrm = take(T * h->d * a);
-  const size_t o_xz = take(T * 2 * h->E * a);
-  const size_t o_xc0 = take(T * h->E * a), o_xc1 = take(T * h->E * a);
-  const size_t o_dbc0 = take(T * h->RP * a), o_dbc1 = take(T * h->RP * a);
+  // Mamba-2 reuses the slots: xz = in_proj output [T, DIPP], xc = conv outputs x|B|C [T, CD], delta = per-direction y [T, E]
+  const size_t w_xz = h->m2 ? h->DIPP : 2 * h->E, w_xc = h->m2 ? h->CD : h->E, w_dbc = h->m2 ? 0 : h->RP;
+  const size_t o_xz = take(T * w_xz * a);
+  const size_t o_xc0 = take(T * w_xc * a), o_xc1 = take(T * w_xc * a);
+  const size_t o_dbc0 = take(T * w_dbc * a), o_dbc1 = take(T * w_dbc * a);
   const size_t o_dl0 = take(T * h->E * a), o_dl1 = take(T * h->E * a);
   const size_t o_y = take(T * h->E * a);
   const size_t ss_parts = static_cast<size_t>(gemm_sumsq_parts(h->d));
@@ -407,6 +387,72 @@ int ensure_workspace(pcad_handle* h, int B, int L) {
   return PCAD_OK;
 }
 
+// ---- Mamba-2 mixer between in_proj and out_proj: conv + SiLU over x|B|C, SSD scan per direction, gated norms + add ------
+int op_ssd_scan(pcad_handle* h, const void* xbc_f, const void* xbc_r, long long ld_xbc, const void* dt_raw, long long ld_dt,
+                const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r, const float* bias_r,
+                void* y_f, void* y_r, int S, int L, int H, bool f32, bool sequential, cudaStream_t st) {
+  if (S <= 0 || L <= 0) return PCAD_OK;
+  if (H <= 0 || S > 65535) return fail(h, PCAD_ERR_INVALID, "ssd_scan: need H > 0 and at most 65535 sequences per call");
+  cudaError_t e;
+  if (f32) {
+    e = launch_ssd_seq<float>(static_cast<const float*>(xbc_f), static_cast<const float*>(xbc_r), ld_xbc, static_cast<const float*>(dt_raw),
+                              ld_dt, A_f, D_f, bias_f, A_r, D_r, bias_r, static_cast<float*>(y_f), static_cast<float*>(y_r), S, L, H, st);
+  } else if (sequential) {
+    e = launch_ssd_seq<bf16>(static_cast<const bf16*>(xbc_f), static_cast<const bf16*>(xbc_r), ld_xbc, static_cast<const bf16*>(dt_raw),
+                             ld_dt, A_f, D_f, bias_f, A_r, D_r, bias_r, static_cast<bf16*>(y_f), static_cast<bf16*>(y_r), S, L, H, st);
+  } else {
+    if ((H & 1) || (ld_xbc % 8) || (reinterpret_cast<uintptr_t>(xbc_f) & 15) || (reinterpret_cast<uintptr_t>(xbc_r) & 15) ||
+        (reinterpret_cast<uintptr_t>(y_f) & 15) || (reinterpret_cast<uintptr_t>(y_r) & 15))
+      return fail(h, PCAD_ERR_INVALID, "ssd_scan: the tensor-core kernel needs an even head count, 16-byte aligned tensors and ld_xbc %% 8 == 0");
+    e = launch_ssd_tc(static_cast<const bf16*>(xbc_f), static_cast<const bf16*>(xbc_r), ld_xbc, static_cast<const bf16*>(dt_raw), ld_dt,
+                      A_f, D_f, bias_f, A_r, D_r, bias_r, static_cast<bf16*>(y_f), static_cast<bf16*>(y_r), S, L, H, st);
+  }
+  CUDA_TRY(h, e);
+  return PCAD_OK;
+}
+
+int op_gated_norm_sum(pcad_handle* h, const void* y_f, const void* y_r, const void* z, long long ldz, const float* w_f,
+                      const float* w_r, void* out, long long rows, int E, float eps, bool f32, cudaStream_t st) {
+  if (rows <= 0) return PCAD_OK;
+  const int vec = f32 ? 4 : 8;
+  if (E % vec || ldz % vec) return fail(h, PCAD_ERR_INVALID, "gated_norm_sum: E and ldz must be multiples of %d", vec);
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  if (f32) gated_norm_sum_kernel<float, true><<<blocks, 256, 0, st>>>(static_cast<const float*>(y_f), static_cast<const float*>(y_r), static_cast<const float*>(z), ldz, w_f, w_r, static_cast<float*>(out), rows, E, eps);
+  else gated_norm_sum_kernel<bf16, false><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(y_f), static_cast<const bf16*>(y_r), static_cast<const bf16*>(z), ldz, w_f, w_r, static_cast<bf16*>(out), rows, E, eps);
+  CUDA_TRY(h, cudaGetLastError());
+  return PCAD_OK;
+}
+
+// ws.xz holds in_proj's output [T, DIPP]: z at [0, E), x|B|C at [E, E + CD), dt at [E + CD, E + CD + H).  Leaves the summed,
+// normed y in ws.y.  [EXT mamba_ssm Mamba2.forward, non-fused branch; BiMambaWrapper "add" with tied projections]
+int run_mixer_m2(pcad_handle* h, LayerWeights& lw, int S, int L, cudaStream_t st) {
+  Workspace& ws = h->ws;
+  const long long T = static_cast<long long>(S) * L;
+  const int E = h->E, CD = h->CD, H = h->H;
+  const bool f32 = h->f32;
+  const size_t a = h->act_size;
+  uint8_t* zx = static_cast<uint8_t*>(ws.xz);
+  int rc;
+  {
+    StageTimer tm(h, st, PCAD_ST_CONV);
+    rc = op_conv(h, zx + static_cast<size_t>(E) * a, h->DIPP, lw.dir[0].conv_w, lw.dir[0].conv_b, lw.dir[1].conv_w, lw.dir[1].conv_b,
+                 ws.xc[0], ws.xc[1], S, L, CD, f32, st);
+    if (rc) return rc;
+  }
+  {
+    StageTimer tm(h, st, PCAD_ST_SCAN);
+    rc = op_ssd_scan(h, ws.xc[0], ws.xc[1], CD, zx + static_cast<size_t>(E + CD) * a, h->DIPP, lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias,
+                     lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.delta[0], ws.delta[1], S, L, H, f32, h->ssd_seq, st);
+    if (rc) return rc;
+  }
+  {
+    StageTimer tm(h, st, PCAD_ST_GNORM);
+    rc = op_gated_norm_sum(h, ws.delta[0], ws.delta[1], zx, h->DIPP, lw.dir[0].gnorm_w, lw.dir[1].gnorm_w, ws.y, T, E, 1e-5f, f32, st);
+    if (rc) return rc;
+  }
+  return PCAD_OK;
+}
+
 // ---- the forward pass over the strand-major layout --------------------------------------------------
 // ids (u8 [B, L]) are already in ws.ids.  Leaves the final normed hidden state in ws.normed.
 int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
@@ -422,6 +468,8 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
   // block is norm kernel -> in_proj ... out_proj -> ws.hid, exactly the reference's order of roundings.
   int cur = 0;
   const int parts = gemm_sumsq_parts(d);
+  const int n_in = h->m2 ? h->DIP : 2 * E;          // in_proj output width and row pitch
+  const long long ld_in = h->m2 ? h->DIPP : 2 * E;
   {
     StageTimer tm(h, st, PCAD_ST_EMBED, fused ? 2 : 1);
     const long long total = T * (d / 8);
@@ -447,42 +495,30 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
         ep.sumsq_parts = parts;
         ep.inv_k = 1.0f / static_cast<float>(d);
         ep.eps = h->cfg.norm_eps;
-        if (h->gate_in_gemm) ep.silu_from = E;   // the z half leaves the GEMM as SiLU(z)
-        rc = op_linear(h, ws.resid, lw.in_proj_s, ws.xz, T, 2 * E, d, d, d, 2 * E, false, h->num_sms, st, kEpiRowScale, ep);
+        rc = op_linear(h, ws.resid, lw.in_proj_s, ws.xz, T, n_in, d, d, d, ld_in, false, h->num_sms, st, kEpiRowScale, ep);
       } else {
-        rc = op_linear(h, ws.normed, lw.in_proj, ws.xz, T, 2 * E, d, d, d, 2 * E, f32, h->num_sms, st);
+        rc = op_linear(h, ws.normed, lw.in_proj, ws.xz, T, n_in, d, d, d, ld_in, f32, h->num_sms, st);
       }
       if (rc) return rc;
     }
-    const bool fuse_cx = h->fuse_conv_xproj && conv_xproj_supported(L, E, RP);
-    if (fuse_cx) {
-      // conv + SiLU for both directions and both x_proj GEMMs in one kernel (conv_xproj.cuh); timed under "conv"
-      StageTimer tm(h, st, PCAD_ST_CONV);
-      rc = op_conv_xproj(h, ws.xz, 2 * E, lw.dir[0].conv_w, lw.dir[0].conv_b, lw.dir[1].conv_w, lw.dir[1].conv_b, ws.xc[0], ws.xc[1],
-                         lw.dir[0].x_proj, lw.dir[1].x_proj, ws.dbc[0], ws.dbc[1], S, L, E, RP, h->num_sms, st);
+    if (h->m2) {
+      rc = run_mixer_m2(h, lw, S, L, st);
       if (rc) return rc;
     } else {
+    {
       StageTimer tm(h, st, PCAD_ST_CONV);
       rc = op_conv(h, ws.xz, 2 * E, lw.dir[0].conv_w, lw.dir[0].conv_b, lw.dir[1].conv_w, lw.dir[1].conv_b, ws.xc[0], ws.xc[1], S, L, E, f32, st);
       if (rc) return rc;
     }
     for (int dir = 0; dir < 2; ++dir) {
-      if (!fuse_cx) {
+      {
         StageTimer tm(h, st, PCAD_ST_X_PROJ);
         rc = op_linear(h, ws.xc[dir], lw.dir[dir].x_proj, ws.dbc[dir], T, RP, E, E, E, RP, f32, h->num_sms, st);
         if (rc) return rc;
       }
       if (!h->fuse_dt) {
         StageTimer tm(h, st, PCAD_ST_DT_PROJ);
-        // Optional (bf16): softplus(dt_proj + bias) in the GEMM epilogue (8 epilogue warps) so the MUFU-bound scan gets
-        // delta ready-made (delta_final).  Default and fp32: the reference's order (raw dt_proj, softplus in the scan).
-        if (h->dt_softplus_epilogue) {
-          EpiParams ep;
-          ep.bias = lw.dir[dir].dt_bias;
-          rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, false, h->num_sms, st, kEpiSoftplus, ep);
-        } else {
-          rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, f32, h->num_sms, st);
-        }
+        rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, f32, h->num_sms, st);
         if (rc) return rc;
       }
     }
@@ -492,13 +528,13 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
       if (h->fuse_dt)   // dt_proj inside the scan: it reads the x_proj outputs (dt | B | C) and the re-laid dt_proj weights
         rc = op_biscan(h, ws.xc[0], ws.dbc[0], ws.dbc[0], ws.xc[1], ws.dbc[1], ws.dbc[1], RP, R, zbase, 2 * E,
                        lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
-                       false, /*z_gated=*/fused && h->gate_in_gemm, st, lw.dir[0].dt_proj_p, lw.dir[1].dt_proj_p);
+                       st, lw.dir[0].dt_proj_p, lw.dir[1].dt_proj_p);
       else
         rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
-                       lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
-                       /*delta_final=*/h->dt_softplus_epilogue, /*z_gated=*/fused && h->gate_in_gemm, st);
+                       lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st);
       if (rc) return rc;
     }
+    }   // Mamba-1 mixer
     {
       StageTimer tm(h, st, PCAD_ST_OUT_PROJ);
       if (fused) {
@@ -563,13 +599,22 @@ const char* pcad_last_error(const pcad_handle* h) { return h ? h->err : g_create
 int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   if (!cfg || !out) return fail(nullptr, PCAD_ERR_INVALID, "null argument");
   *out = nullptr;
-  if (cfg->d_state != 16) return fail(nullptr, PCAD_ERR_INVALID, "unsupported d_state=%d (engine is specialised for 16)", cfg->d_state);
+  const bool m2 = cfg->mixer == PCAD_MIXER_MAMBA2;
+  if (cfg->mixer != PCAD_MIXER_MAMBA1 && !m2) return fail(nullptr, PCAD_ERR_INVALID, "unknown mixer %d", cfg->mixer);
+  if (m2) {
+    if (cfg->d_state != 64 || cfg->headdim != 64 || cfg->ngroups != 1)
+      return fail(nullptr, PCAD_ERR_INVALID, "unsupported Mamba-2 shape d_state=%d headdim=%d ngroups=%d (engine is specialised for 64 / 64 / 1)",
+                  cfg->d_state, cfg->headdim, cfg->ngroups);
+    if ((cfg->expand * cfg->d_model / 64) % 2) return fail(nullptr, PCAD_ERR_INVALID, "Mamba-2 needs an even number of heads");
+  } else if (cfg->d_state != 16) {
+    return fail(nullptr, PCAD_ERR_INVALID, "unsupported d_state=%d (engine is specialised for 16)", cfg->d_state);
+  }
   if (cfg->d_conv != 4) return fail(nullptr, PCAD_ERR_INVALID, "unsupported d_conv=%d (engine is specialised for 4)", cfg->d_conv);
   if (cfg->vocab_size != 8) return fail(nullptr, PCAD_ERR_INVALID, "unsupported vocab_size=%d (LM head is specialised for 8 rows)", cfg->vocab_size);
   if (cfg->d_model <= 0 || cfg->d_model % 128 != 0 || cfg->d_model > 2048)
     return fail(nullptr, PCAD_ERR_INVALID, "unsupported d_model=%d (need a multiple of 128, <= 2048)", cfg->d_model);
   if (cfg->expand != 2) return fail(nullptr, PCAD_ERR_INVALID, "unsupported expand=%d", cfg->expand);
-  if (cfg->dt_rank <= 0 || cfg->dt_rank % 8 != 0) return fail(nullptr, PCAD_ERR_INVALID, "unsupported dt_rank=%d (need a multiple of 8)", cfg->dt_rank);
+  if (!m2 && (cfg->dt_rank <= 0 || cfg->dt_rank % 8 != 0)) return fail(nullptr, PCAD_ERR_INVALID, "unsupported dt_rank=%d (need a multiple of 8)", cfg->dt_rank);
   if (cfg->n_layer < 0) return fail(nullptr, PCAD_ERR_INVALID, "negative n_layer");
   if (cfg->dtype != PCAD_BF16 && cfg->dtype != PCAD_F32) return fail(nullptr, PCAD_ERR_INVALID, "dtype must be PCAD_BF16 or PCAD_F32");
   for (int i = 0; i < cfg->vocab_size; ++i)
@@ -596,26 +641,25 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   h->N = cfg->d_state;
   h->R = cfg->dt_rank;
   h->RP = (h->R + 2 * h->N + 15) / 16 * 16;
+  h->m2 = m2;
+  if (m2) {
+    h->H = h->E / 64;
+    h->CD = h->E + 2 * h->N;
+    h->DIP = h->E + h->CD + h->H;
+    h->DIPP = (h->DIP + 7) / 8 * 8;
+    h->R = 0;
+    h->RP = 0;
+    if (const char* sq = getenv("PCAD_SSD_SEQ")) h->ssd_seq = sq[0] == '1';
+  }
   h->V = cfg->vocab_size;
   h->f32 = cfg->dtype == PCAD_F32;
   h->act_size = h->f32 ? 4 : 2;
   h->fuse_norm = !h->f32 && !cfg->residual_in_fp32;
-  h->fuse_conv_xproj = false;   // measured slower than conv + 2 x_proj GEMMs (see conv_xproj.cuh); opt-in for experiments
-  if (const char* fc = getenv("PCAD_FUSED_CONV_XPROJ")) h->fuse_conv_xproj = !h->f32 && fc[0] == '1';
-  // Off by default: measured zero-sum on B200 (l32, B = 256: scan -11.5 ms, dt_proj +12.3 ms per step), so the
-  // forward keeps the reference's order of operations; PCAD_DT_SOFTPLUS_EPILOGUE=1 switches it on for experiments.
-  h->dt_softplus_epilogue = false;
-  if (const char* ds = getenv("PCAD_DT_SOFTPLUS_EPILOGUE")) h->dt_softplus_epilogue = !h->f32 && ds[0] == '1';
   // dt_proj inside the scan kernel (bf16; x_proj output rows must hold at least 64 columns for the TMA box).
-  // Off by default: measured slower on B200 (scan +30 ms, dt_proj -12.5 ms per step; see scan.cuh).
+  // Off by default: measured slower on B200 (scan +21 ms, dt_proj -12 ms per step; see scan.cuh).
   h->fuse_dt = false;
   if (const char* fd = getenv("PCAD_FUSED_DT"))
-    h->fuse_dt = fd[0] == '1' && !h->f32 && !h->dt_softplus_epilogue && h->RP >= kScanDtK && h->R <= kScanDtK && (h->E % 8) == 0;
-  // SiLU(z) in in_proj's epilogue + a multiply-only scan epilogue.  Off by default: measured zero-sum on B200 (l32,
-  // B = 256: scan -3.4 ms, in_proj +2.9 ms per step -- the forward runs under the power cap, so moving MUFU work
-  // between kernels does not shorten it), and the default keeps the reference's order of operations.
-  h->gate_in_gemm = false;
-  if (const char* gg = getenv("PCAD_GATE_IN_GEMM")) h->gate_in_gemm = h->fuse_norm && (h->E % 64) == 0 && gg[0] == '1';
+    h->fuse_dt = fd[0] == '1' && !m2 && !h->f32 && h->RP >= kScanDtK && h->R <= kScanDtK && (h->E % 8) == 0;
   if (const char* nf = getenv("PCAD_NO_FUSED_NORM")) { if (nf[0] == '1') h->fuse_norm = false; }   // A/B switch for tests
   memset(h->prof_ms, 0, sizeof(h->prof_ms));
   memset(h->prof_launches, 0, sizeof(h->prof_launches));
@@ -642,13 +686,23 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
       h->bad_flag = static_cast<int*>(dp);
     }
   }
+  const size_t n_in_rows = m2 ? static_cast<size_t>(h->DIP) : static_cast<size_t>(2) * h->E;
   for (auto& lw : h->layers) {
-    rc |= A8(&lw.in_proj, static_cast<size_t>(2) * h->E * h->d * a);
-    if (h->fuse_norm) rc |= A8(&lw.in_proj_s, static_cast<size_t>(2) * h->E * h->d * a);
+    rc |= A8(&lw.in_proj, n_in_rows * h->d * a);
+    if (h->fuse_norm) rc |= A8(&lw.in_proj_s, n_in_rows * h->d * a);
     rc |= A8(&lw.out_proj, static_cast<size_t>(h->d) * h->E * a);
     rc |= dev_alloc(h, &lw.norm_w, h->d);
     for (int dir = 0; dir < 2; ++dir) {
       DirWeights& dw = lw.dir[dir];
+      if (m2) {
+        rc |= dev_alloc(h, &dw.conv_w, static_cast<size_t>(h->CD) * 4);
+        rc |= dev_alloc(h, &dw.conv_b, h->CD);
+        rc |= dev_alloc(h, &dw.dt_bias, h->H);
+        rc |= dev_alloc(h, &dw.A, h->H);
+        rc |= dev_alloc(h, &dw.D, h->H);
+        rc |= dev_alloc(h, &dw.gnorm_w, h->E);
+        continue;
+      }
       rc |= dev_alloc(h, &dw.conv_w, static_cast<size_t>(h->E) * 4);
       rc |= dev_alloc(h, &dw.conv_b, h->E);
       rc |= A8(&dw.x_proj, static_cast<size_t>(h->RP) * h->E * a);
@@ -753,11 +807,14 @@ int pcad_set_weight(pcad_handle* h, const char* name, const void* data, const in
   const std::string leaf = rest.substr(mp.size() + 4);
   DirWeights& dw = lw.dir[dir];
   int rc;
+  const int n_in = h->m2 ? h->DIP : 2 * E;        // in_proj rows
+  const int CE = h->m2 ? h->CD : E;               // channels through the conv
+  const int NH = h->m2 ? h->H : E;                // Mamba-2: dt_bias / A_log / D are per head
   if (leaf == "in_proj.weight") {
-    if (!shape_is(shape, ndim, {2 * E, d})) return bad_shape();
+    if (!shape_is(shape, ndim, {n_in, d})) return bad_shape();
     // tied to mamba_fwd (bidirectional_weight_tie); a de-duplicated checkpoint may carry only the mamba_rev name
     if (dir == 1 && lw.has_in) return PCAD_OK;
-    rc = ingest(h, data, src_dtype, lw.in_proj, h->f32, 2LL * E * d);
+    rc = ingest(h, data, src_dtype, lw.in_proj, h->f32, static_cast<long long>(n_in) * d);
     lw.has_in = rc == PCAD_OK;
   } else if (leaf == "out_proj.weight") {
     if (!shape_is(shape, ndim, {d, E})) return bad_shape();
@@ -765,38 +822,42 @@ int pcad_set_weight(pcad_handle* h, const char* name, const void* data, const in
     rc = ingest(h, data, src_dtype, lw.out_proj, h->f32, static_cast<long long>(d) * E);
     lw.has_out = rc == PCAD_OK;
   } else if (leaf == "conv1d.weight") {
-    if (!shape_is(shape, ndim, {E, 4})) return bad_shape();
-    rc = ingest(h, data, src_dtype, dw.conv_w, true, static_cast<long long>(E) * 4);
+    if (!shape_is(shape, ndim, {CE, 4})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.conv_w, true, static_cast<long long>(CE) * 4);
     dw.has[0] = rc == PCAD_OK;
   } else if (leaf == "conv1d.bias") {
-    if (!shape_is(shape, ndim, {E})) return bad_shape();
-    rc = ingest(h, data, src_dtype, dw.conv_b, true, E);
+    if (!shape_is(shape, ndim, {CE})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.conv_b, true, CE);
     dw.has[1] = rc == PCAD_OK;
-  } else if (leaf == "x_proj.weight") {
+  } else if (leaf == "x_proj.weight" && !h->m2) {
     if (!shape_is(shape, ndim, {R + 2 * N, E})) return bad_shape();
     rc = ingest(h, data, src_dtype, dw.x_proj, h->f32, static_cast<long long>(R + 2 * N) * E);  // rows beyond stay zero
     dw.has[2] = rc == PCAD_OK;
-  } else if (leaf == "dt_proj.weight") {
+  } else if (leaf == "dt_proj.weight" && !h->m2) {
     if (!shape_is(shape, ndim, {E, R})) return bad_shape();
     rc = ingest(h, data, src_dtype, dw.dt_proj, h->f32, static_cast<long long>(E) * R);
     dw.has[3] = rc == PCAD_OK;
-  } else if (leaf == "dt_proj.bias") {
-    if (!shape_is(shape, ndim, {E})) return bad_shape();
-    rc = ingest(h, data, src_dtype, dw.dt_bias, true, E);
+  } else if ((leaf == "dt_proj.bias" && !h->m2) || (leaf == "dt_bias" && h->m2)) {
+    if (!shape_is(shape, ndim, {NH})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.dt_bias, true, NH);
     dw.has[4] = rc == PCAD_OK;
   } else if (leaf == "A_log") {
-    if (!shape_is(shape, ndim, {E, N})) return bad_shape();
-    rc = ingest(h, data, src_dtype, dw.A, true, static_cast<long long>(E) * N);
+    const long long n = h->m2 ? NH : static_cast<long long>(E) * N;
+    if (h->m2 ? !shape_is(shape, ndim, {NH}) : !shape_is(shape, ndim, {E, N})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.A, true, n);
     if (rc == PCAD_OK) {
-      const long long n = static_cast<long long>(E) * N;
       neg_exp_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(dw.A, n);  // A = -exp(A_log), fp32
       CUDA_TRY(h, cudaDeviceSynchronize());
     }
     dw.has[5] = rc == PCAD_OK;
   } else if (leaf == "D") {
-    if (!shape_is(shape, ndim, {E})) return bad_shape();
-    rc = ingest(h, data, src_dtype, dw.D, true, E);
+    if (!shape_is(shape, ndim, {NH})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.D, true, NH);
     dw.has[6] = rc == PCAD_OK;
+  } else if (leaf == "norm.weight" && h->m2) {
+    if (!shape_is(shape, ndim, {E})) return bad_shape();
+    rc = ingest(h, data, src_dtype, dw.gnorm_w, true, E);
+    dw.has[7] = rc == PCAD_OK;
   } else {
     return fail(h, PCAD_ERR_INVALID, "unknown weight name %s", name);
   }
@@ -815,19 +876,21 @@ int pcad_finalize(pcad_handle* h) {
     CUDA_TRY(h, cudaDeviceSynchronize());
     h->has_head = true;
   }
-  static const char* names[7] = {"conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight", "dt_proj.bias", "A_log", "D"};
+  static const char* names1[8] = {"conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight", "dt_proj.bias", "A_log", "D", nullptr};
+  static const char* names2[8] = {"conv1d.weight", "conv1d.bias", nullptr, nullptr, "dt_bias", "A_log", "D", "norm.weight"};
+  const char** names = h->m2 ? names2 : names1;
   for (int li = 0; li < h->cfg.n_layer; ++li) {
     const LayerWeights& lw = h->layers[li];
     if (!lw.has_in) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d in_proj.weight", li);
     if (!lw.has_out) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d out_proj.weight", li);
     if (!lw.has_norm) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d norm.weight", li);
     for (int dir = 0; dir < 2; ++dir)
-      for (int k = 0; k < 7; ++k)
-        if (!lw.dir[dir].has[k]) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d mamba_%s.%s", li, dir ? "rev" : "fwd", names[k]);
+      for (int k = 0; k < 8; ++k)
+        if (names[k] && !lw.dir[dir].has[k]) return fail(h, PCAD_ERR_MISSING, "missing weight: layers.%d mamba_%s.%s", li, dir ? "rev" : "fwd", names[k]);
   }
   if (h->fuse_norm) {
     CUDA_TRY(h, cudaSetDevice(h->device));
-    const long long rows = 2LL * h->E, n = rows * h->d;
+    const long long rows = h->m2 ? h->DIP : 2LL * h->E, n = rows * h->d;
     for (auto& lw : h->layers)
       scale_columns_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(static_cast<const bf16*>(lw.in_proj), lw.norm_w,
                                                                            static_cast<bf16*>(lw.in_proj_s), rows, h->d);
@@ -1074,13 +1137,6 @@ int pcad_op_linear(const void* A, const void* W, void* C, int64_t M, int N, int 
   return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, dtype == PCAD_F32, op_num_sms(), static_cast<cudaStream_t>(stream)));
 }
 
-int pcad_op_linear_softplus(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream) {
-  if (dtype != PCAD_BF16 || !bias) return PCAD_ERR_INVALID;
-  EpiParams ep;
-  ep.bias = bias;
-  return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiSoftplus, ep));
-}
-
 int pcad_op_linear_residual(const void* A, const void* W, const void* resid_in, void* resid_out, float* sumsq_out, int64_t M, int N, int K,
                             int64_t lda, int64_t ldw, int64_t ld_res, int dtype, void* stream) {
   if (dtype != PCAD_BF16 || !resid_in || !sumsq_out) return PCAD_ERR_INVALID;
@@ -1103,18 +1159,6 @@ int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in,
   return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiRowScale, ep));
 }
 
-int pcad_op_linear_rowscale_silu(const void* A, const void* W, const float* sumsq_in, int sumsq_parts, float eps, int silu_from, void* C,
-                                 int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldc, int dtype, void* stream) {
-  if (dtype != PCAD_BF16 || !sumsq_in || sumsq_parts < 1 || silu_from < 0) return PCAD_ERR_INVALID;
-  EpiParams ep;
-  ep.sumsq_in = sumsq_in;
-  ep.sumsq_parts = sumsq_parts;
-  ep.inv_k = 1.0f / static_cast<float>(K);
-  ep.eps = eps;
-  ep.silu_from = silu_from;
-  return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiRowScale, ep));
-}
-
 int pcad_op_prep_dt_weight(const void* W, int64_t ldw, void* out, int E, int R, void* stream) {
   if (!W || !out || E <= 0 || R <= 0 || R > kScanDtK || ldw < R) return PCAD_ERR_INVALID;
   const long long n = static_cast<long long>(E) * kScanDtK;
@@ -1126,11 +1170,10 @@ int pcad_op_prep_dt_weight(const void* W, int64_t ldw, void* out, int E, int R, 
 int pcad_op_biscan_dt(const void* u_f, const void* dbc_f, const void* u_r, const void* dbc_r, int64_t ldbc, int bc_off,
                       const void* wdt_f, const void* wdt_r, const void* z, int64_t ldz, const float* A_f, const float* D_f,
                       const float* dt_bias_f, const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E,
-                      int flags, void* stream) {
-  if (!wdt_f || !wdt_r || (flags & 1)) return PCAD_ERR_INVALID;
+                      void* stream) {
+  if (!wdt_f || !wdt_r) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_biscan(op_scratch(), u_f, dbc_f, dbc_f, u_r, dbc_r, dbc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
-                                     A_r, D_r, dt_bias_r, y, S, L, E, false, false, (flags & 2) != 0, static_cast<cudaStream_t>(stream),
-                                     wdt_f, wdt_r));
+                                     A_r, D_r, dt_bias_r, y, S, L, E, false, static_cast<cudaStream_t>(stream), wdt_f, wdt_r));
 }
 
 int pcad_op_add_rmsnorm(const void* x, const void* res_in, const float* w, void* y, void* res_out, int64_t rows, int d, float eps, int dtype, int res_dtype, void* stream) {
@@ -1144,21 +1187,27 @@ int pcad_op_conv_silu(const void* x, int64_t ldx, const float* w_f, const float*
   return op_fail_to_global(op_conv(op_scratch(), x, ldx, w_f, b_f, w_r, b_r, out_f, out_r, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream)));
 }
 
-int pcad_op_conv_xproj(const void* x, int64_t ldx, const float* w_f, const float* b_f, const float* w_r, const float* b_r,
-                       void* out_f, void* out_r, const void* wx_f, const void* wx_r, void* dbc_f, void* dbc_r,
-                       int S, int L, int E, int RP, int dtype, void* stream) {
-  if (dtype != PCAD_BF16) return PCAD_ERR_INVALID;
-  return op_fail_to_global(op_conv_xproj(op_scratch(), x, ldx, w_f, b_f, w_r, b_r, out_f, out_r, wx_f, wx_r, dbc_f, dbc_r, S, L, E, RP,
-                                         op_num_sms(), static_cast<cudaStream_t>(stream)));
-}
-
 int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f, const void* u_r, const void* delta_r, const void* bc_r,
                    int64_t ldbc, int bc_off, const void* z, int64_t ldz, const float* A_f, const float* D_f, const float* dt_bias_f,
-                   const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E, int delta_final, int dtype, void* stream) {
+                   const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E, int dtype, void* stream) {
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_biscan(op_scratch(), u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
-                                     A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, (delta_final & 1) != 0, (delta_final & 2) != 0,
-                                     static_cast<cudaStream_t>(stream)));
+                                     A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream)));
+}
+
+int pcad_op_ssd_scan(const void* xbc_f, const void* xbc_r, int64_t ld_xbc, const void* dt_raw, int64_t ld_dt, const float* A_f,
+                     const float* D_f, const float* dt_bias_f, const float* A_r, const float* D_r, const float* dt_bias_r, void* y_f,
+                     void* y_r, int S, int L, int H, int dtype, int sequential, void* stream) {
+  if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_ssd_scan(op_scratch(), xbc_f, xbc_r, ld_xbc, dt_raw, ld_dt, A_f, D_f, dt_bias_f, A_r, D_r, dt_bias_r, y_f,
+                                       y_r, S, L, H, dtype == PCAD_F32, sequential != 0, static_cast<cudaStream_t>(stream)));
+}
+
+int pcad_op_gated_norm_sum(const void* y_f, const void* y_r, const void* z, int64_t ldz, const float* w_f, const float* w_r, void* out,
+                           int64_t rows, int E, float eps, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_gated_norm_sum(op_scratch(), y_f, y_r, z, ldz, w_f, w_r, out, rows, E, eps, dtype == PCAD_F32,
+                                             static_cast<cudaStream_t>(stream)));
 }
 
 }  // extern "C"

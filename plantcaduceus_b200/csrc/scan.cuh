@@ -33,12 +33,11 @@
 // (e) every instruction outside the main loop counts (the kernel issues at ~0.65 IPC): loads are TMA, the B|C
 //     conversion is one 4-value group per thread, the epilogue and the prefetch of parked partials have branch-free
 //     block-uniform fast paths;
-// (f) kScanPoly of the 8 pair-exponentials can come from an FMA-pipe polynomial with the multiply folded into the
-//     range reduction (exp2_prod_poly2) instead of MUFU.EX2.  Default 0.  Measured at l32, B = 256 with the final
-//     kernel structure: 0 -> 5.08 ms per launch, 1 -> 5.11, 2 -> 5.33; packed FFMA2 with three distinct operands
-//     runs at ~2.7 cycles, so a polynomial pair costs more issue/FMA time than the MUFU time it frees
-//     (profiles/r01_scan_step_ub.txt).  Giving whole warps a polynomial flavour, a software-pipelined step and an
-//     in-loop park/finalise (no epilogue phase) were also built and measured: none beat this configuration.
+// Built, measured and removed (profiles/r01_scan_step_ub.txt): FMA-pipe polynomial exponentials for part of the 8 pairs
+// (packed FFMA2 with three distinct operands runs at ~2.7 cycles, so a polynomial pair costs more issue/FMA time than the
+// MUFU time it frees: 5.11 / 5.33 ms with 1 / 2 of 8 pairs against 5.08), whole-warp polynomial flavours, a
+// software-pipelined step, an in-loop park/finalise, softplus in dt_proj's epilogue and SiLU(z) in in_proj's (both zero-sum
+// under the power cap).
 #pragma once
 
 #include <stdlib.h>
@@ -58,10 +57,6 @@ constexpr int kScanCH = PCAD_SCAN_CH;     // channels per CTA (128, or 64: small
 constexpr int kScanSeg8 = kScanCH / 8;    // 8-channel (16-byte bf16) segments per row
 constexpr int kScanThreads = 2 * kScanCH;
 constexpr int kScanN = 16;       // d_state
-#ifndef PCAD_SCAN_POLY
-#define PCAD_SCAN_POLY 0
-#endif
-constexpr int kScanPoly = PCAD_SCAN_POLY;   // pairs (of 8) whose exp2 runs on the FMA pipe
 #ifndef PCAD_SCAN_SPPOLY
 #define PCAD_SCAN_SPPOLY 7   // 0: softplus through MUFU.EX2 + MUFU.LG2; 6 / 7: log2(1 + e) from a polynomial with that many coefficients
 #endif
@@ -129,8 +124,6 @@ template <> struct ScanDir<true> {
   static __device__ __forceinline__ float b_scale() { return 1.0f; }
   // returns d (natural units)
   __device__ __forceinline__ float delta(float raw) const { return softplus<true>(raw + bias); }
-  __device__ __forceinline__ float delta_final(float d) const { return d; }
-  template <int NPOLY>
   __device__ __forceinline__ float step(float d, float du, float y0, const float* bc) {
     float y = y0;
 #pragma unroll
@@ -145,26 +138,13 @@ template <> struct ScanDir<true> {
 template <> struct ScanDir<false> {
   f32x2 h[kScanN / 2], a[kScanN / 2];   // a = A (log2 domain: multiplied by d' = d / ln 2)
   float bias_l2;   // bias * log2(e)
-  float dclamp;    // polynomial pairs: d' is clamped so that d' * A >= -126 (2^-126 is 0 for the recurrence)
-  template <int NPOLY>
-  static constexpr __device__ __forceinline__ bool is_poly(int p) {
-    // the first NPOLY pairs of the order 1, 4, 6, 3, 0, 5, 2, 7 (spread over the 8, so that polynomial and MUFU
-    // pairs alternate in the instruction stream)
-    constexpr int order[8] = {1, 4, 6, 3, 0, 5, 2, 7};
-    for (int i = 0; i < NPOLY && i < 8; ++i)
-      if (order[i] == p) return true;
-    return false;
-  }
   __device__ __forceinline__ void init(const float* A, float bias_) {
     bias_l2 = bias_ * kLog2e;
-    float amax = 1e-30f;
 #pragma unroll
     for (int p = 0; p < kScanN / 2; ++p) {
       h[p] = pack2(0.f, 0.f);
       a[p] = A ? pack2(A[2 * p], A[2 * p + 1]) : pack2(0.f, 0.f);
-      if (A) amax = fmaxf(amax, fmaxf(fabsf(A[2 * p]), fabsf(A[2 * p + 1])));
     }
-    dclamp = 126.0f / amax;
   }
   static __device__ __forceinline__ float b_scale() { return kLn2; }   // B is pre-multiplied by ln 2
   // returns d' = softplus(raw + bias) / ln 2  (identity above 20, as the reference)
@@ -196,14 +176,8 @@ template <> struct ScanDir<false> {
     return xl > 20.0f * kLog2e ? xl : sp;
 #endif
   }
-  // delta already softplus'ed (dt_proj's softplus epilogue): only the change of units
-  __device__ __forceinline__ float delta_final(float d) const { return d * kLog2e; }
-  template <int NPOLY>
   __device__ __forceinline__ float step(float d, float du, float y0, const float* bc) {
     const f32x2 dd = pack2(d, d), duu = pack2(du, du);
-    float dc = d;
-    if (NPOLY > 0) dc = fminf(d, dclamp);
-    const f32x2 ddc = pack2(dc, dc);
     const ulonglong2* bc2 = reinterpret_cast<const ulonglong2*>(bc);   // 16 bytes = two (n, n+1) pairs
     f32x2 acc[2] = {pack2(y0, 0.f), pack2(0.f, 0.f)};   // two chains: the FFMA2 -> FFMA2 latency is exposed otherwise
 #pragma unroll
@@ -213,14 +187,9 @@ template <> struct ScanDir<false> {
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const int p = 2 * g + k;
-        f32x2 dA;
-        if (is_poly<NPOLY>(p)) {
-          dA = exp2_prod_poly2(ddc, a[p]);
-        } else {
-          float x0, x1;
-          unpack2(mul2(dd, a[p]), x0, x1);
-          dA = pack2(ex2_approx(x0), ex2_approx(x1));
-        }
+        float x0, x1;
+        unpack2(mul2(dd, a[p]), x0, x1);
+        const f32x2 dA = pack2(ex2_approx(x0), ex2_approx(x1));
         h[p] = fma2(dA, h[p], mul2(duu, Bp[k]));
         acc[k] = fma2(h[p], Cp[k], acc[k]);
       }
@@ -231,9 +200,6 @@ template <> struct ScanDir<false> {
   }
 };
 
-// DFINAL: delta_* already hold softplus(dt_proj + bias) (the GEMM's softplus epilogue); bias_* are ignored.
-// ZGATED: z already holds SiLU(z) (in_proj's row-scale epilogue with silu_from): the epilogue only multiplies.
-//
 // Staging.  u, delta and B|C of both directions arrive by TMA: six 3-D tensor maps [sequence][row][channel] with a
 // [1][16][128] (B|C: [1][16][32]) box, issued by one thread per chunk into a 2-stage ring and completed on an
 // mbarrier, so the other 255 threads spend no instructions on loads and rows outside [0, L) (ragged last chunk,
@@ -250,7 +216,7 @@ template <> struct ScanDir<false> {
 // grows by 21 ms (30 with 128-channel blocks): the weight fragments fit neither the registers nor the shared memory
 // that 4 blocks/SM leave, so every chunk re-reads them from L2 and the warp waits out that latency with the MUFU pipe
 // idle (block order does not change it).  Opt-in (PCAD_FUSED_DT=1).
-template <typename T, bool PRECISE, bool DFINAL, bool ZGATED, bool FUSEDT>
+template <typename T, bool PRECISE, bool FUSEDT>
 __global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : (kScanCH == 64 ? PCAD_SCAN_MINBLOCKS64 : PCAD_SCAN_MINBLOCKS))
 biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__ CUtensorMap tm_df,
               const __grid_constant__ CUtensorMap tm_bcf, const __grid_constant__ CUtensorMap tm_ur,
@@ -259,7 +225,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
               const T* __restrict__ z, long long ldz, const float* __restrict__ A_f, const float* __restrict__ D_f,
               const float* __restrict__ bias_f, const float* __restrict__ A_r, const float* __restrict__ D_r,
               const float* __restrict__ bias_r, T* y, int L, int E) {
-  static_assert(!FUSEDT || (sizeof(T) == 2 && !PRECISE && !DFINAL), "the in-kernel dt_proj is a bf16-path feature");
+  static_assert(!FUSEDT || (sizeof(T) == 2 && !PRECISE), "the in-kernel dt_proj is a bf16-path feature");
   extern __shared__ __align__(128) uint8_t scan_smem_raw[];
   // TMA destinations must be 128-byte aligned (1024 for the swizzled dt tiles); the runtime only promises 16 for the
   // dynamic segment (pointer arithmetic on the array itself, so that the accesses stay in the shared address space)
@@ -438,14 +404,14 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
         float dl;
         {
           const float draw = ActT<T>::to_f(dp[drow(0)]);
-          dl = DFINAL ? S.delta_final(draw) : S.delta(draw);
+          dl = S.delta(draw);
         }
         auto advance = [&](int j) -> float {
           const int jn = min(j + 1, kScanTC - 1);
           const float uu_n = ActT<T>::to_f(up[row(jn)]);
           const float draw_n = ActT<T>::to_f(dp[drow(jn)]);
-          const float dl_n = DFINAL ? S.delta_final(draw_n) : S.delta(draw_n);
-          const float yv = S.template step<kScanPoly>(dl, dl * uu, Dskip * uu, bcp + j * 2 * kScanN);
+          const float dl_n = S.delta(draw_n);
+          const float yv = S.step(dl, dl * uu, Dskip * uu, bcp + j * 2 * kScanN);
           uu = uu_n;
           dl = dl_n;
           return yv;
@@ -497,13 +463,10 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
               for (int q = 0; q < 4; ++q) {
                 const f32x2 p2 = pack2(__uint_as_float(pw[q] << 16), __uint_as_float(pw[q] & 0xffff0000u));
                 const f32x2 z2 = pack2(__uint_as_float(zw[q] << 16), __uint_as_float(zw[q] & 0xffff0000u));
-                f32x2 g2 = z2;   // ZGATED: already SiLU(z)
-                if constexpr (!ZGATED) {
-                  float x0, x1, d0, d1;
-                  unpack2(mul2(z2, nl2), x0, x1);
-                  unpack2(add2(pack2(ex2_approx(x0), ex2_approx(x1)), one2), d0, d1);
-                  g2 = mul2(z2, pack2(rcp_approx(d0), rcp_approx(d1)));   // SiLU(z)
-                }
+                float x0, x1, d0, d1;
+                unpack2(mul2(z2, nl2), x0, x1);
+                unpack2(add2(pack2(ex2_approx(x0), ex2_approx(x1)), one2), d0, d1);
+                const f32x2 g2 = mul2(z2, pack2(rcp_approx(d0), rcp_approx(d1)));   // SiLU(z)
                 v2[q] = mul2(add2(v2[q], p2), g2);
               }
             }
@@ -549,7 +512,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
       float zz[VEC];
       load16<T>(&sm.pz[1][dd][j][seg * VEC], zz);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) v[k] *= ZGATED ? zz[k] : silu<PRECISE>(zz[k]);
+      for (int k = 0; k < VEC; ++k) v[k] *= silu<PRECISE>(zz[k]);
       store16<T>(yp, v);
     }
     // no barrier here: the next iteration's first __syncthreads orders these reads of sm.ys and of the stage
@@ -570,7 +533,7 @@ __global__ void prep_dt_weight_kernel(const bf16* __restrict__ W, long long ldw,
 
 // FUSEDT = true: delta_f / delta_r are the x_proj outputs ([S*L, ldbc], dt in columns 0..R-1, ldbc >= 64) and wdt_f / wdt_r
 // the weights from prep_dt_weight_kernel; otherwise delta_* are [S*L, E] and wdt_* unused.
-template <typename T, bool PRECISE, bool DFINAL, bool ZGATED = false, bool FUSEDT = false>
+template <typename T, bool PRECISE, bool FUSEDT = false>
 inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, const T* u_r, const T* delta_r,
                                  const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
@@ -579,7 +542,7 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
   size_t smem = sizeof(ScanShared<T, FUSEDT>) + (FUSEDT ? 1024 : 128);   // + alignment slack for the TMA destinations
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static unsigned long long attr_done = 0;
-  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, DFINAL, ZGATED, FUSEDT>, static_cast<int>(smem), attr_done);
+  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, FUSEDT>, static_cast<int>(smem), attr_done);
   if (e1 != cudaSuccess) return e1;
   constexpr bool f32 = sizeof(T) == 4;
   CUtensorMap tm[6];
@@ -596,7 +559,7 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
   ok = ok && make_tmap_3d(&tm[5], f32, bc_r + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
   if (!ok) return cudaErrorInvalidValue;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
-  biscan_kernel<T, PRECISE, DFINAL, ZGATED, FUSEDT><<<grid, kScanThreads, smem, stream>>>(
+  biscan_kernel<T, PRECISE, FUSEDT><<<grid, kScanThreads, smem, stream>>>(
       tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], wdt_f, wdt_r, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E);
   return cudaGetLastError();
 }

@@ -147,6 +147,8 @@ class CaduceusForMaskedLM:
         pc.norm_eps = float(cfg.norm_epsilon)
         pc.residual_in_fp32 = int(bool(cfg.residual_in_fp32))
         pc.dtype = _TORCH_TO_PCAD[self.dtype]
+        pc.mixer = _lib.PCAD_MIXER_MAMBA2 if cfg.is_mamba2 else _lib.PCAD_MIXER_MAMBA1
+        pc.headdim, pc.ngroups = cfg.headdim, cfg.ngroups
         for i in range(16):
             pc.complement_map[i] = int(cfg.complement_map.get(i, i)) if i < cfg.vocab_size else i
         h = C.c_void_p()

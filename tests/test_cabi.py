@@ -31,7 +31,7 @@ def test_header_and_binding_agree(lib):
     assert sorted(_lib.EXPORTS) == syms, (set(syms) ^ set(_lib.EXPORTS))
     for s in syms:
         assert hasattr(lib, s), f"libpcad.so does not export {s}"
-    assert lib.pcad_abi_version() == 1
+    assert lib.pcad_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback(lib):
@@ -49,6 +49,9 @@ def test_no_cpu_fallback(lib):
     # unsupported configuration is rejected before any device work
     cfg.d_state = 8
     assert lib.pcad_create(C.byref(cfg), 0, C.byref(h)) == -1
+    cfg.d_state, cfg.mixer = 16, 1                      # Mamba-2 needs d_state 64 / headdim 64 / ngroups 1
+    assert lib.pcad_create(C.byref(cfg), 0, C.byref(h)) == -1
+    assert b"Mamba-2" in lib.pcad_last_error(None)
     from plantcaduceus_b200.modeling import CaduceusForMaskedLM
     from plantcaduceus_b200 import CaduceusConfig
     m = CaduceusForMaskedLM.from_random(CaduceusConfig(d_model=128, n_layer=1))

@@ -111,7 +111,7 @@ def test_biscan_matches_mamba_ssm_kernel_port(cuda_device, S, L, E, R):
     z_ptr = C.c_void_p(xz_d.data_ptr() + E * 4)
     rc = lib.pcad_op_biscan(ptr(u_d[0]), ptr(dl_d[0]), ptr(bc_d[0]), ptr(u_d[1]), ptr(dl_d[1]), ptr(bc_d[1]), RP, R, z_ptr,
                             2 * E, ptr(A_d[0]), ptr(D_d[0]), ptr(b_d[0]), ptr(A_d[1]), ptr(D_d[1]), ptr(b_d[1]), ptr(y),
-                            S, L, E, 0, F32, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                            S, L, E, F32, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, lib.pcad_last_error(None)
     torch.cuda.synchronize()
 
@@ -134,57 +134,10 @@ def test_biscan_matches_mamba_ssm_kernel_port(cuda_device, S, L, E, R):
     assert (y - want).abs().max().item() <= 1e-4 * scale + 1e-5
 
 
-# ---- conv1d + SiLU and fused add + RMSNorm against vLLM's kernels (library code, checker only) --------------------
-def _vllm_conv(x_bel, w, b):
-    """vLLM's causal_conv1d_fn (its port of causal-conv1d's varlen forward): x [b, E, L] -> SiLU(conv) [b, E, L]."""
-    try:
-        from vllm.model_executor.layers.mamba.ops.causal_conv1d import causal_conv1d_fn
-    except Exception as e:  # pragma: no cover
-        pytest.skip(f"vLLM causal_conv1d_fn not importable: {type(e).__name__}: {e}")
-    bsz, E, L = x_bel.shape
-    K = w.shape[1]
-    flat = x_bel.permute(1, 0, 2).reshape(E, bsz * L).contiguous()
-    # the kernel wants a (dim, tokens) VIEW with unit stride along dim ("channel-last")
-    flat = flat.t().contiguous().t()
-    conv_states = torch.zeros(bsz, K - 1, E, device=x_bel.device, dtype=x_bel.dtype).transpose(1, 2)
-    qsl = torch.arange(0, (bsz + 1) * L, L, device=x_bel.device, dtype=torch.int32)
-    try:
-        out = causal_conv1d_fn(flat, w.contiguous(), b.contiguous(), conv_states, qsl,
-                               cache_indices=torch.arange(bsz, device=x_bel.device, dtype=torch.int32),
-                               has_initial_state=torch.zeros(bsz, device=x_bel.device, dtype=torch.bool),
-                               activation="silu")
-        torch.cuda.synchronize()
-    except Exception as e:
-        pytest.skip(f"vLLM causal_conv1d_fn refused the call on this build: {type(e).__name__}: {e}")
-    return out.reshape(E, bsz, L).permute(1, 0, 2)
-
-
-@pytest.mark.parametrize("S,L,E", [(2, 512, 256), (3, 70, 128)])
-def test_conv_silu_matches_vllm_causal_conv1d(cuda_device, S, L, E):
-    """pcad_op_conv_silu (fp32): forward taps == the library kernel on x, reverse taps == the library kernel on the
-    time-flipped x, flipped back.  Also pins the oracle's F.conv1d restatement to the same kernel."""
-    from plantcaduceus_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(S + L + E)
-    x = torch.randn(S * L, E, generator=g).to(cuda_device)
-    w = [(torch.rand(E, 4, generator=g) - 0.5).to(cuda_device) for _ in range(2)]
-    b = [(torch.rand(E, generator=g) - 0.5).to(cuda_device) for _ in range(2)]
-    out = [torch.full((S * L, E), float("nan"), device=cuda_device) for _ in range(2)]
-    ptr = lambda t: C.c_void_p(t.data_ptr())
-    rc = lib.pcad_op_conv_silu(ptr(x), E, ptr(w[0]), ptr(b[0]), ptr(w[1]), ptr(b[1]), ptr(out[0]), ptr(out[1]), S, L, E, F32,
-                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    assert rc == 0, lib.pcad_last_error(None)
-    torch.cuda.synchronize()
-    x_bel = x.reshape(S, L, E).transpose(1, 2).contiguous()
-    want_f = _vllm_conv(x_bel, w[0], b[0]).transpose(1, 2).reshape(S * L, E)
-    want_r = _vllm_conv(x_bel.flip(-1).contiguous(), w[1], b[1]).flip(-1).transpose(1, 2).reshape(S * L, E)
-    assert (out[0] - want_f).abs().max().item() <= 1e-5 * max(1.0, want_f.abs().max().item())
-    assert (out[1] - want_r).abs().max().item() <= 1e-5 * max(1.0, want_r.abs().max().item())
-    # the oracle's restatement (oracle.mamba_mixer's conv line) against the same kernel
-    xc = F.conv1d(x_bel.cpu(), w[0].cpu()[:, None, :], b[0].cpu(), padding=3, groups=E)[..., :L]
-    assert (F.silu(xc) - want_f.reshape(S, L, E).transpose(1, 2).cpu()).abs().max().item() <= 1e-5
-
-
+# ---- fused add + RMSNorm against vLLM's CUDA kernel (library code, checker only) ---------------------------------------
+# (vLLM's causal_conv1d_fn is a Triton re-implementation with a continuous-batching calling convention, not a port of the
+# causal-conv1d CUDA kernel; the conv is pinned instead, together with the whole mixer, by transformers' MambaMixer /
+# Mamba2Mixer in tests/test_oracle.py.)
 @pytest.mark.parametrize("rows,d", [(300, 384), (64, 1024)])
 def test_add_rmsnorm_matches_vllm_fused_add_rms_norm(cuda_device, rows, d):
     """pcad_op_add_rmsnorm (fp32) == torch.ops._C.fused_add_rms_norm (in place: residual <- x + residual,

@@ -71,7 +71,7 @@ def main():
         y = torch.empty(T, E, **bf)
         def f():
             rc = lib.pcad_op_biscan(ptr(u_f), ptr(dl_f), ptr(bc_f), ptr(u_r), ptr(dl_r), ptr(bc_r), RP, R, ptr(z), 2 * E,
-                                    ptr(A), ptr(Dp), ptr(bias), ptr(A2), ptr(Dp), ptr(bias), ptr(y), S, L, E, args.delta_final, BF16, st)
+                                    ptr(A), ptr(Dp), ptr(bias), ptr(A2), ptr(Dp), ptr(bias), ptr(y), S, L, E, BF16, st)
             assert rc == 0, lib.pcad_last_error(None)
         ms = timeit(f)
         out["scan_ms"] = ms
@@ -89,21 +89,6 @@ def main():
         out["conv_ms"] = ms
         out["conv_GBs"] = T * E * 2 * 3 / ms / 1e6
         del xz, of, orv
-    if "conv_xproj" in ops:
-        xz = rnd(T, 2 * E)
-        w = torch.randn(E, 4, device=dev, generator=g)
-        b = torch.randn(E, device=dev, generator=g)
-        wx = rnd(RP, E, scale=E ** -0.5)
-        of, orv = torch.empty(T, E, **bf), torch.empty(T, E, **bf)
-        df, dr = torch.empty(T, RP, **bf), torch.empty(T, RP, **bf)
-        def f():
-            rc = lib.pcad_op_conv_xproj(ptr(xz), 2 * E, ptr(w), ptr(b), ptr(w), ptr(b), ptr(of), ptr(orv), ptr(wx), ptr(wx),
-                                        ptr(df), ptr(dr), S, L, E, RP, BF16, st)
-            assert rc == 0, lib.pcad_last_error(None)
-        ms = timeit(f)
-        out["conv_xproj_ms"] = ms
-        out["conv_xproj_GBs"] = T * E * 2 * 3 / ms / 1e6
-        del xz, of, orv, df, dr
     if "norm" in ops:
         x, r = rnd(T, d), rnd(T, d)
         w = torch.ones(d, device=dev)
@@ -125,10 +110,7 @@ def main():
         Cm = torch.empty(T, ldc, **bf)
         gbias = torch.full((Nn,), -4.0, device=dev)
         def f():
-            if name == "dt_proj" and args.delta_final:
-                rc = lib.pcad_op_linear_softplus(ptr(Amat), ptr(W), ptr(gbias), ptr(Cm), T, Nn, K, lda, ldw, ldc, BF16, st)
-            else:
-                rc = lib.pcad_op_linear(ptr(Amat), ptr(W), ptr(Cm), T, Nn, K, lda, ldw, ldc, BF16, st)
+            rc = lib.pcad_op_linear(ptr(Amat), ptr(W), ptr(Cm), T, Nn, K, lda, ldw, ldc, BF16, st)
             assert rc == 0, lib.pcad_last_error(None)
         ms = timeit(f)
         out[name + "_ms"] = ms
