@@ -202,6 +202,19 @@ int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f,
                    const float* A_r, const float* D_r, const float* dt_bias_r,
                    void* y, int S, int L, int E, int dtype, void* stream);
 
+/* pcad_op_biscan as a TIME-PARALLEL scan (low batch / long context): every sequence is cut into `segments` pieces of
+ * L / segments positions (L % segments == 0, segments >= 2) that are scanned concurrently -- each from a zero state to get
+ * its end state, the end states combined in scan order into every segment's start state, then the segments scanned again from
+ * those states.  Exact up to fp32 rounding of the carry.  seg_state: float [S * segments * 2 * E * 16] scratch, seg_sumd: float
+ * [S * segments * 2 * E] scratch.  The forward selects this by itself when E / 64 * S CTAs would leave the GPU mostly idle. */
+int pcad_op_biscan_segmented(const void* u_f, const void* delta_f, const void* bc_f,
+                             const void* u_r, const void* delta_r, const void* bc_r,
+                             int64_t ldbc, int bc_off, const void* z, int64_t ldz,
+                             const float* A_f, const float* D_f, const float* dt_bias_f,
+                             const float* A_r, const float* D_r, const float* dt_bias_r,
+                             void* y, int S, int L, int E, int segments, float* seg_state, float* seg_sumd,
+                             int dtype, void* stream);
+
 /* The same with Mamba.dt_proj [F.linear(dt, dt_proj.weight)] computed inside the scan kernel (bf16 only): dbc_* are the
  * x_proj outputs [S*L, ldbc] (dt in columns [0, R), B at [bc_off, bc_off+16), C at [bc_off+16, bc_off+32); ldbc >= 64),
  * wdt_* the dt_proj weights re-laid by pcad_op_prep_dt_weight ([E, R] with row pitch ldw -> [E, 64], R <= 64).  Delta is

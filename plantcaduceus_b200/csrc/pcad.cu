@@ -60,6 +60,8 @@ struct Workspace {
   void* delta[2] = {nullptr, nullptr};  // [T, E]
   void* y = nullptr;           // [T, E]
   float* sumsq[2] = {nullptr, nullptr};  // [T, parts] per-column-tile sums of squares of the residual stream (fused-norm path)
+  float* seg_state = nullptr;  // time-parallel scan: [S*P, 2, E, 16] segment states
+  float* seg_sumd = nullptr;   // time-parallel scan: [S*P, 2, E] sums of delta
   uint8_t* ascii = nullptr;    // [B, L] staging for the host entry
   float* logits4 = nullptr;    // [B, 4] staging for the host entry
   int* pos = nullptr;          // [B] staging for the host entry
@@ -95,6 +97,15 @@ struct pcad_handle {
   int acgt[4] = {3, 4, 5, 6};
   Workspace ws;
   std::vector<void*> allocs;
+  // CUDA graphs of the score-only forward for small batches (launch-bound: ~260 launches of a few microseconds each):
+  // one executable graph per (B, L, token_idx), captured on the second call with that shape, replayed afterwards.
+  struct ScoreGraph { int B, L, token_idx; bool seen_only; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<ScoreGraph> graphs;
+  bool time_parallel = true;            // Mamba-1: segmented scan when the sequential kernel's grid leaves the SMs empty
+  bool use_graphs = true;
+  cudaStream_t gstream = nullptr;       // capture / replay stream (the caller's may be the legacy default stream, which cannot capture)
+  cudaEvent_t g_in = nullptr, g_out = nullptr;
+  long long graph_max_tokens = 65536;   // strand-tokens (2 B L) up to which a forward is replayed from a graph
   // profiling
   bool profiling = false;
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> prof_events;
@@ -309,7 +320,8 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
               const void* delta_r, const void* bc_r, long long ldbc, int bc_off, const void* z, long long ldz,
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
               const float* bias_r, void* y, int S, int L, int E, bool f32, cudaStream_t st,
-              const void* wdt_f = nullptr, const void* wdt_r = nullptr) {
+              const void* wdt_f = nullptr, const void* wdt_r = nullptr, int segments = 1, float* seg_state = nullptr,
+              float* seg_sumd = nullptr) {
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
     return fail(h, PCAD_ERR_INVALID, "biscan: E, ldbc, bc_off, ldz must be multiples of %d elements", vec);
@@ -319,16 +331,24 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
 #define PCAD_SCAN_ARGS(TT)                                                                                           \
   static_cast<const TT*>(u_f), static_cast<const TT*>(delta_f), static_cast<const TT*>(bc_f), static_cast<const TT*>(u_r), \
       static_cast<const TT*>(delta_r), static_cast<const TT*>(bc_r), ldbc, bc_off, static_cast<const TT*>(z), ldz, A_f, D_f, \
-      bias_f, A_r, D_r, bias_r, static_cast<TT*>(y), S, L, E, st
+      bias_f, A_r, D_r, bias_r, static_cast<TT*>(y), S, L, E
   const bool fused_dt = wdt_f != nullptr || wdt_r != nullptr;
+  if (segments > 1) {   // time-parallel: `segments` concurrent segments per sequence (scan.cuh)
+    if (fused_dt || !seg_state || !seg_sumd || L % segments || static_cast<long long>(S) * segments > 65535)
+      return fail(h, PCAD_ERR_INVALID, "biscan: the time-parallel scan needs L %% segments == 0, S * segments <= 65535 and its state buffers");
+    if (f32) e = launch_biscan_time_parallel<float, true>(PCAD_SCAN_ARGS(float), segments, seg_state, seg_sumd, st);
+    else e = launch_biscan_time_parallel<bf16, false>(PCAD_SCAN_ARGS(bf16), segments, seg_state, seg_sumd, st);
+    CUDA_TRY(h, e);
+    return PCAD_OK;
+  }
   if (fused_dt) {   // delta_* are the x_proj outputs, dt_proj runs inside the kernel
     if (f32 || !wdt_f || !wdt_r || ldbc < kScanDtK)
       return fail(h, PCAD_ERR_INVALID, "biscan: the in-kernel dt_proj needs bf16, both weights and ldbc >= 64");
-    e = launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16), static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r));
+    e = launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16), st, static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r));
   } else if (f32) {
-    e = launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float));
+    e = launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float), st);
   } else {
-    e = launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16));
+    e = launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16), st);
   }
 #undef PCAD_SCAN_ARGS
   CUDA_TRY(h, e);
@@ -337,6 +357,7 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
 
 // ---- workspace ------------------------------------------------------------------------------------
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t kSegStateBytes = 16u << 20;   // time-parallel scan: room for S * P * 2 * E * 16 floats at low batch
 
 size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
   const size_t T = 2ull * B * L;
@@ -357,6 +378,7 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
   const size_t o_y = take(T * h->E * a);
   const size_t ss_parts = static_cast<size_t>(gemm_sumsq_parts(h->d));
   const size_t o_ss0 = take(T * ss_parts * sizeof(float)), o_ss1 = take(T * ss_parts * sizeof(float));
+  const size_t o_segs = take(h->m2 ? 0 : kSegStateBytes), o_segd = take(h->m2 ? 0 : kSegStateBytes / 16);
   const size_t o_ascii = take(static_cast<size_t>(B) * L);
   const size_t o_l4 = take(static_cast<size_t>(B) * 4 * sizeof(float));
   const size_t o_pos = take(static_cast<size_t>(B) * sizeof(int));
@@ -366,15 +388,23 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
     ws->xc[0] = p + o_xc0; ws->xc[1] = p + o_xc1; ws->dbc[0] = p + o_dbc0; ws->dbc[1] = p + o_dbc1;
     ws->delta[0] = p + o_dl0; ws->delta[1] = p + o_dl1; ws->y = p + o_y;
     ws->sumsq[0] = reinterpret_cast<float*>(p + o_ss0); ws->sumsq[1] = reinterpret_cast<float*>(p + o_ss1);
+    ws->seg_state = reinterpret_cast<float*>(p + o_segs); ws->seg_sumd = reinterpret_cast<float*>(p + o_segd);
     ws->ascii = p + o_ascii; ws->logits4 = reinterpret_cast<float*>(p + o_l4); ws->pos = reinterpret_cast<int*>(p + o_pos);
   }
   return off;
+}
+
+void clear_graphs(pcad_handle* h) {
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
 }
 
 int ensure_workspace(pcad_handle* h, int B, int L) {
   Workspace& ws = h->ws;
   const size_t need = workspace_layout(h, B, L, nullptr);
   if (ws.base == nullptr || need > ws.bytes) {
+    clear_graphs(h);   // captured launches point into the old allocation
     if (ws.base) { cudaDeviceSynchronize(); cudaFree(ws.base); ws.base = nullptr; ws.bytes = 0; }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, need);
@@ -417,6 +447,22 @@ int op_gated_norm_sum(pcad_handle* h, const void* y_f, const void* y_r, const vo
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldz % vec) return fail(h, PCAD_ERR_INVALID, "gated_norm_sum: E and ldz must be multiples of %d", vec);
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  if (!f32 && E <= 256 * 12) {   // bf16: the row stays in registers between the statistics and the output
+    const int ch = (E + 255) / 256;
+#define GN_CASE(CHV)                                                                                                        \
+  gated_norm_sum_regs_kernel<CHV><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(y_f), static_cast<const bf16*>(y_r),        \
+                                                          static_cast<const bf16*>(z), ldz, w_f, w_r, static_cast<bf16*>(out), rows, E, eps)
+    if (ch <= 1) GN_CASE(1);
+    else if (ch <= 2) GN_CASE(2);
+    else if (ch <= 3) GN_CASE(3);
+    else if (ch <= 4) GN_CASE(4);
+    else if (ch <= 6) GN_CASE(6);
+    else if (ch <= 8) GN_CASE(8);
+    else GN_CASE(12);
+#undef GN_CASE
+    CUDA_TRY(h, cudaGetLastError());
+    return PCAD_OK;
+  }
   if (f32) gated_norm_sum_kernel<float, true><<<blocks, 256, 0, st>>>(static_cast<const float*>(y_f), static_cast<const float*>(y_r), static_cast<const float*>(z), ldz, w_f, w_r, static_cast<float*>(out), rows, E, eps);
   else gated_norm_sum_kernel<bf16, false><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(y_f), static_cast<const bf16*>(y_r), static_cast<const bf16*>(z), ldz, w_f, w_r, static_cast<bf16*>(out), rows, E, eps);
   CUDA_TRY(h, cudaGetLastError());
@@ -529,9 +575,21 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
         rc = op_biscan(h, ws.xc[0], ws.dbc[0], ws.dbc[0], ws.xc[1], ws.dbc[1], ws.dbc[1], RP, R, zbase, 2 * E,
                        lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
                        st, lw.dir[0].dt_proj_p, lw.dir[1].dt_proj_p);
-      else
+      else {
+        // low batch / long context: cut every sequence into P concurrent segments while the sequential kernel's grid
+        // (E / 64 x S CTAs) would leave resident slots (4 per SM) empty and the segments stay >= 128 steps long
+        int P = 1;
+        if (h->time_parallel) {
+          const long long ctas = static_cast<long long>((E + kScanCH - 1) / kScanCH) * S, slots = 4LL * h->num_sms;
+          while (P < 32 && ctas * P * 2 <= slots && L % (P * 2) == 0 && L / (P * 2) >= 128 &&
+                 static_cast<size_t>(S) * P * 2 * 2 * E * kScanN * sizeof(float) <= kSegStateBytes)
+            P *= 2;
+        }
         rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
-                       lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st);
+                       lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st,
+                       nullptr, nullptr, P, ws.seg_state, ws.seg_sumd);
+        if (P > 1) h->launch_count += 2;
+      }
       if (rc) return rc;
     }
     }   // Mamba-1 mixer
@@ -660,6 +718,9 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   h->fuse_dt = false;
   if (const char* fd = getenv("PCAD_FUSED_DT"))
     h->fuse_dt = fd[0] == '1' && !m2 && !h->f32 && h->RP >= kScanDtK && h->R <= kScanDtK && (h->E % 8) == 0;
+  if (const char* tp = getenv("PCAD_NO_TIME_PARALLEL")) h->time_parallel = tp[0] != '1';
+  if (const char* ng = getenv("PCAD_NO_GRAPH")) h->use_graphs = ng[0] != '1';
+  if (const char* gm = getenv("PCAD_GRAPH_MAX_TOKENS")) h->graph_max_tokens = atoll(gm);
   if (const char* nf = getenv("PCAD_NO_FUSED_NORM")) { if (nf[0] == '1') h->fuse_norm = false; }   // A/B switch for tests
   memset(h->prof_ms, 0, sizeof(h->prof_ms));
   memset(h->prof_launches, 0, sizeof(h->prof_launches));
@@ -738,6 +799,10 @@ void pcad_destroy(pcad_handle* h) {
   cudaDeviceSynchronize();
   for (auto& pe : h->prof_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
   for (auto ev : h->event_pool) cudaEventDestroy(ev);
+  clear_graphs(h);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->g_in) cudaEventDestroy(h->g_in);
+  if (h->g_out) cudaEventDestroy(h->g_out);
   if (h->ws.base) cudaFree(h->ws.base);
   if (h->bad_flag_host) cudaFreeHost(const_cast<int*>(h->bad_flag_host));
   for (void* p : h->allocs) cudaFree(p);
@@ -755,6 +820,7 @@ int pcad_set_tokenizer(pcad_handle* h, const uint8_t lut[256], int mask_id, cons
   CUDA_TRY(h, cudaMemcpy(h->sel_dev, sel, sizeof(sel), cudaMemcpyHostToDevice));
   h->mask_id = mask_id;
   for (int k = 0; k < 4; ++k) h->acgt[k] = acgt_ids[k];
+  clear_graphs(h);   // mask id and column selection are baked into captured launches
   return PCAD_OK;
 }
 
@@ -763,6 +829,7 @@ int pcad_set_weight(pcad_handle* h, const char* name, const void* data, const in
   if (src_dtype != PCAD_BF16 && src_dtype != PCAD_F32 && src_dtype != PCAD_F16) return fail(h, PCAD_ERR_INVALID, "bad src_dtype for %s", name);
   CUDA_TRY(h, cudaSetDevice(h->device));
   h->finalized = false;
+  clear_graphs(h);
   const int d = h->d, E = h->E, N = h->N, R = h->R, V = h->V;
   const std::string s(name);
   auto bad_shape = [&]() { return fail(h, PCAD_ERR_INVALID, "unexpected shape for %s", name); };
@@ -943,6 +1010,73 @@ int pcad_extract_windows(pcad_handle* h, const uint8_t* chrom_dev, int64_t chrom
   return PCAD_OK;
 }
 
+namespace {
+// tokenise + mask (ws.ascii -> ws.ids), backbone, head at token_idx -> ws.logits4; everything on `st`, internal buffers only
+int score_core(pcad_handle* h, int B, int L, int token_idx, cudaStream_t st) {
+  Workspace& ws = h->ws;
+  const long long n = static_cast<long long>(B) * L;
+  {
+    StageTimer tm(h, st, PCAD_ST_MISC, 2);
+    tokenize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ascii, ws.ids, n, h->lut_dev, L, token_idx, h->mask_id);
+    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos, B, token_idx);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  int rc = run_backbone(h, B, L, st);
+  if (rc) return rc;
+  return run_head(h, B, L, ws.pos, 1, ws.logits4, st);
+}
+
+// The same through a CUDA graph when the forward is small enough to be launch-bound.  First call with a shape: eager (also
+// sets the kernels' shared-memory attributes, which must not happen inside a capture); second: capture + instantiate;
+// then replay.  Profiling (per-stage events) always runs eagerly.
+int score_core_graphed(pcad_handle* h, int B, int L, int token_idx, cudaStream_t st) {
+  if (!h->use_graphs || h->profiling || 2LL * B * L > h->graph_max_tokens) return score_core(h, B, L, token_idx, st);
+  pcad_handle::ScoreGraph* e = nullptr;
+  for (auto& g : h->graphs)
+    if (g.B == B && g.L == L && g.token_idx == token_idx) { e = &g; break; }
+  if (!e) {
+    h->graphs.push_back({B, L, token_idx, true, nullptr, 0});
+    return score_core(h, B, L, token_idx, st);
+  }
+  if (!h->gstream) {
+    if (cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->g_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->g_out, cudaEventDisableTiming) != cudaSuccess) {
+      h->use_graphs = false;
+      cudaGetLastError();
+      return score_core(h, B, L, token_idx, st);
+    }
+  }
+  if (e->seen_only) {
+    const int64_t before = h->launch_count;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeThreadLocal);
+    int rc = ce == cudaSuccess ? score_core(h, B, L, token_idx, h->gstream) : PCAD_ERR_CUDA;
+    if (ce == cudaSuccess) ce = cudaStreamEndCapture(h->gstream, &graph);
+    if (rc == PCAD_OK && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != PCAD_OK || ce != cudaSuccess || !e->exec) {
+      e->exec = nullptr;
+      h->use_graphs = false;                       // fall back to eager launches for good; this call still has to run
+      h->launch_count = before;
+      cudaGetLastError();
+      return score_core(h, B, L, token_idx, st);
+    }
+    e->launches = h->launch_count - before;
+    h->launch_count = before;
+    e->seen_only = false;
+  }
+  // replay on the capture stream, ordered after / before the caller's stream by events
+  CUDA_TRY(h, cudaEventRecord(h->g_in, st));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->gstream, h->g_in, 0));
+  CUDA_TRY(h, cudaGraphLaunch(e->exec, h->gstream));
+  CUDA_TRY(h, cudaEventRecord(h->g_out, h->gstream));
+  CUDA_TRY(h, cudaStreamWaitEvent(st, h->g_out, 0));
+  h->launch_count += e->launches;
+  return PCAD_OK;
+}
+}  // namespace
+
 int pcad_score_windows_dev(pcad_handle* h, const uint8_t* ascii_dev, int B, int L, int token_idx, float* logits4_dev, void* stream) {
   int rc = check_call(h, B, L);
   if (rc) return rc;
@@ -954,16 +1088,12 @@ int pcad_score_windows_dev(pcad_handle* h, const uint8_t* ascii_dev, int B, int 
   rc = ensure_workspace(h, B, L);
   if (rc) return rc;
   Workspace& ws = h->ws;
-  const long long n = static_cast<long long>(B) * L;
-  {
-    StageTimer tm(h, st, PCAD_ST_MISC, 2);
-    tokenize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ascii_dev, ws.ids, n, h->lut_dev, L, token_idx, h->mask_id);
-    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos, B, token_idx);
-    CUDA_TRY(h, cudaGetLastError());
-  }
-  rc = run_backbone(h, B, L, st);
+  const size_t n = static_cast<size_t>(B) * L;
+  CUDA_TRY(h, cudaMemcpyAsync(ws.ascii, ascii_dev, n, cudaMemcpyDeviceToDevice, st));
+  rc = score_core_graphed(h, B, L, token_idx, st);
   if (rc) return rc;
-  return run_head(h, B, L, ws.pos, 1, logits4_dev, st);
+  CUDA_TRY(h, cudaMemcpyAsync(logits4_dev, ws.logits4, static_cast<size_t>(B) * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return PCAD_OK;
 }
 
 int pcad_forward(pcad_handle* h, const int64_t* ids_dev, int B, int L, float* logits_dev, void* hidden_dev, void* stream) {
@@ -1056,17 +1186,8 @@ int pcad_score_windows_host(pcad_handle* h, const uint8_t* ascii_host, int B, in
   rc = ensure_workspace(h, B, L);
   if (rc) return rc;
   Workspace& ws = h->ws;
-  const long long n = static_cast<long long>(B) * L;
-  CUDA_TRY(h, cudaMemcpyAsync(ws.ascii, ascii_host, n, cudaMemcpyHostToDevice, st));
-  {
-    StageTimer tm(h, st, PCAD_ST_MISC, 2);
-    tokenize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ascii, ws.ids, n, h->lut_dev, L, token_idx, h->mask_id);
-    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos, B, token_idx);
-    CUDA_TRY(h, cudaGetLastError());
-  }
-  rc = run_backbone(h, B, L, st);
-  if (rc) return rc;
-  rc = run_head(h, B, L, ws.pos, 1, ws.logits4, st);
+  CUDA_TRY(h, cudaMemcpyAsync(ws.ascii, ascii_host, static_cast<size_t>(B) * L, cudaMemcpyHostToDevice, st));
+  rc = score_core_graphed(h, B, L, token_idx, st);
   if (rc) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(logits4_host, ws.logits4, static_cast<size_t>(B) * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
@@ -1193,6 +1314,16 @@ int pcad_op_biscan(const void* u_f, const void* delta_f, const void* bc_f, const
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_biscan(op_scratch(), u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
                                      A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream)));
+}
+
+int pcad_op_biscan_segmented(const void* u_f, const void* delta_f, const void* bc_f, const void* u_r, const void* delta_r, const void* bc_r,
+                             int64_t ldbc, int bc_off, const void* z, int64_t ldz, const float* A_f, const float* D_f, const float* dt_bias_f,
+                             const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E, int segments,
+                             float* seg_state, float* seg_sumd, int dtype, void* stream) {
+  if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
+  return op_fail_to_global(op_biscan(op_scratch(), u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
+                                     A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream), nullptr,
+                                     nullptr, segments, seg_state, seg_sumd));
 }
 
 int pcad_op_ssd_scan(const void* xbc_f, const void* xbc_r, int64_t ld_xbc, const void* dt_raw, int64_t ld_dt, const float* A_f,

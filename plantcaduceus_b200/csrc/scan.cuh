@@ -122,6 +122,16 @@ template <> struct ScanDir<true> {
     for (int n = 0; n < kScanN; ++n) { h[n] = 0.f; a[n] = A ? A[n] : 0.f; }
   }
   static __device__ __forceinline__ float b_scale() { return 1.0f; }
+  __device__ __forceinline__ void load_state(const float* p) {
+#pragma unroll
+    for (int n = 0; n < kScanN; ++n) h[n] = p[n];
+  }
+  __device__ __forceinline__ void store_state(float* p) const {
+#pragma unroll
+    for (int n = 0; n < kScanN; ++n) p[n] = h[n];
+  }
+  // decay of a state over a run of steps whose delta values (in this class's units) sum to sd
+  __device__ __forceinline__ float run_decay(float sd, int n) const { return expf(sd * a[n]); }
   // returns d (natural units)
   __device__ __forceinline__ float delta(float raw) const { return softplus<true>(raw + bias); }
   __device__ __forceinline__ float step(float d, float du, float y0, const float* bc) {
@@ -147,6 +157,19 @@ template <> struct ScanDir<false> {
     }
   }
   static __device__ __forceinline__ float b_scale() { return kLn2; }   // B is pre-multiplied by ln 2
+  __device__ __forceinline__ void load_state(const float* p) {
+#pragma unroll
+    for (int q = 0; q < kScanN / 2; ++q) h[q] = pack2(p[2 * q], p[2 * q + 1]);
+  }
+  __device__ __forceinline__ void store_state(float* p) const {
+#pragma unroll
+    for (int q = 0; q < kScanN / 2; ++q) unpack2(h[q], p[2 * q], p[2 * q + 1]);
+  }
+  __device__ __forceinline__ float run_decay(float sd, int n) const {
+    float a0, a1;
+    unpack2(a[n >> 1], a0, a1);
+    return ex2_approx(sd * ((n & 1) ? a1 : a0));
+  }
   // returns d' = softplus(raw + bias) / ln 2  (identity above 20, as the reference)
   __device__ __forceinline__ float delta(float raw) const {
     const float xl = fmaf(raw, kLog2e, bias_l2);
@@ -224,7 +247,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
               const T* __restrict__ wdt_f, const T* __restrict__ wdt_r,
               const T* __restrict__ z, long long ldz, const float* __restrict__ A_f, const float* __restrict__ D_f,
               const float* __restrict__ bias_f, const float* __restrict__ A_r, const float* __restrict__ D_r,
-              const float* __restrict__ bias_r, T* y, int L, int E) {
+              const float* __restrict__ bias_r, T* y, int L, int E, const float* __restrict__ h0) {
   static_assert(!FUSEDT || (sizeof(T) == 2 && !PRECISE), "the in-kernel dt_proj is a bf16-path feature");
   extern __shared__ __align__(128) uint8_t scan_smem_raw[];
   // TMA destinations must be 128-byte aligned (1024 for the swizzled dt tiles); the runtime only promises 16 for the
@@ -284,6 +307,8 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     const float* A = dir ? A_r : A_f;
     const float* bias = dir ? bias_r : bias_f;
     S.init(active ? A + e * kScanN : nullptr, active ? bias[e] : 0.f);
+    // time-parallel mode: this "sequence" is one segment of a longer one and starts from the carried state
+    if (h0 != nullptr && active) S.load_state(h0 + ((static_cast<long long>(blockIdx.y) * 2 + dir) * E + e) * kScanN);
   }
   const float Dskip = active ? (dir ? D_r : D_f)[e] : 0.f;
   const float bscale = ScanDir<PRECISE>::b_scale();
@@ -538,7 +563,8 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
                                  const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
                                  const float* D_r, const float* bias_r, T* y, int S, int L, int E,
-                                 cudaStream_t stream, const T* wdt_f = nullptr, const T* wdt_r = nullptr) {
+                                 cudaStream_t stream, const T* wdt_f = nullptr, const T* wdt_r = nullptr,
+                                 const float* h0 = nullptr) {
   size_t smem = sizeof(ScanShared<T, FUSEDT>) + (FUSEDT ? 1024 : 128);   // + alignment slack for the TMA destinations
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static unsigned long long attr_done = 0;
@@ -560,8 +586,127 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
   if (!ok) return cudaErrorInvalidValue;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
   biscan_kernel<T, PRECISE, FUSEDT><<<grid, kScanThreads, smem, stream>>>(
-      tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], wdt_f, wdt_r, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E);
+      tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], wdt_f, wdt_r, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E, h0);
   return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Time-parallel scan for low batch / long context (BASELINE.json north_star: chunk-local scan -> carry combine -> fix-up).
+// biscan_kernel is sequential in time with one CTA per (sequence, 64 channels): at B = 1 that is E / 64 x 2 CTAs for 592
+// resident slots.  Here a sequence of length L is cut into P segments that are scanned concurrently:
+//   1. scan_segment_state_kernel: every segment from a ZERO state, keeping only its end state h_end0 and the sum of its
+//      deltas (the segment's total decay per state is exp(A sum(delta)): the recurrence is linear in h);
+//   2. scan_segment_carry_kernel: the P end states of a (sequence, direction, channel) combined in scan order,
+//      h_in(k+1) = decay_k h_in(k) + h_end0(k) -- a serial chain of P steps on 16 values;
+//   3. biscan_kernel on the segments as [S P] "sequences" of length L / P, each starting from its h_in.
+// The exponentials are evaluated twice (passes 1 and 3), so this pays only while the grid of the sequential kernel leaves
+// the machine empty; pcad.cu picks P so that E / 64 x S x P just fills the resident slots.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T, bool PRECISE>
+__global__ void __launch_bounds__(kScanThreads)
+scan_segment_state_kernel(const T* __restrict__ u_f, const T* __restrict__ delta_f, const T* __restrict__ bc_f,
+                          const T* __restrict__ u_r, const T* __restrict__ delta_r, const T* __restrict__ bc_r, long long ldbc,
+                          int bc_off, const float* __restrict__ A_f, const float* __restrict__ bias_f,
+                          const float* __restrict__ A_r, const float* __restrict__ bias_r, float* __restrict__ hend,
+                          float* __restrict__ sumd, int Lseg, int E) {
+  __shared__ __align__(16) float sbc[2][kScanTC][2 * kScanN];
+  const int tid = threadIdx.x;
+  const int dir = tid / kScanCH, ch = tid & (kScanCH - 1);
+  const int e = blockIdx.x * kScanCH + ch;
+  const bool active = e < E;
+  const long long row0 = static_cast<long long>(blockIdx.y) * Lseg;     // blockIdx.y = sequence * P + segment
+  const T* u = dir ? u_r : u_f;
+  const T* dl = dir ? delta_r : delta_f;
+  ScanDir<PRECISE> S;
+  S.init(active ? (dir ? A_r : A_f) + e * kScanN : nullptr, active ? (dir ? bias_r : bias_f)[e] : 0.f);
+  const float bscale = ScanDir<PRECISE>::b_scale();
+  float sd = 0.f;
+  for (int i0 = 0; i0 < Lseg; i0 += kScanTC) {
+    const int nst = min(kScanTC, Lseg - i0);
+    __syncthreads();
+    for (int idx = tid; idx < 2 * kScanTC * 2 * kScanN; idx += kScanThreads) {
+      const int dd = idx / (kScanTC * 2 * kScanN), rem = idx % (kScanTC * 2 * kScanN);
+      const int j = rem / (2 * kScanN), k = rem % (2 * kScanN);
+      float v = 0.f;
+      if (j < nst) {
+        const long long r = row0 + (dd ? Lseg - 1 - (i0 + j) : i0 + j);
+        v = ActT<T>::to_f((dd ? bc_r : bc_f)[r * ldbc + bc_off + k]);
+      }
+      sbc[dd][j][k] = k < kScanN ? v * bscale : v;
+    }
+    float uu[kScanTC], dr[kScanTC];
+#pragma unroll
+    for (int j = 0; j < kScanTC; ++j) {
+      const long long r = row0 + (dir ? Lseg - 1 - (i0 + j) : i0 + j);
+      const bool ok = active && j < nst;
+      uu[j] = ok ? ActT<T>::to_f(u[r * E + e]) : 0.f;
+      dr[j] = ok ? ActT<T>::to_f(dl[r * E + e]) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < kScanTC; ++j) {
+        if (j < nst) {
+          const float d = S.delta(dr[j]);
+          sd += d;
+          S.step(d, d * uu[j], 0.f, &sbc[dir][j][0]);
+        }
+      }
+    }
+  }
+  if (active) {
+    const long long o = (static_cast<long long>(blockIdx.y) * 2 + dir) * E + e;
+    S.store_state(hend + o * kScanN);
+    sumd[o] = sd;
+  }
+}
+
+// hend [S*P][2][E][16] -> in place: the state each segment STARTS from.  One thread per (sequence, direction, channel).
+template <bool PRECISE>
+__global__ void scan_segment_carry_kernel(const float* __restrict__ A_f, const float* __restrict__ A_r, float* __restrict__ hend,
+                                          const float* __restrict__ sumd, int S, int P, int E) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(S) * 2 * E) return;
+  const int e = static_cast<int>(gid % E);
+  const int dir = static_cast<int>((gid / E) % 2);
+  const int seq = static_cast<int>(gid / (2LL * E));
+  ScanDir<PRECISE> D;
+  D.init((dir ? A_r : A_f) + e * kScanN, 0.f);
+  float carry[kScanN];
+#pragma unroll
+  for (int n = 0; n < kScanN; ++n) carry[n] = 0.f;
+  for (int k = 0; k < P; ++k) {
+    const int seg = dir ? P - 1 - k : k;                       // scan order of the segments
+    const long long o = ((static_cast<long long>(seq) * P + seg) * 2 + dir) * E + e;
+    float* hp = hend + o * kScanN;
+    const float sd = sumd[o];
+#pragma unroll
+    for (int n = 0; n < kScanN; ++n) {
+      const float end0 = hp[n];
+      hp[n] = carry[n];
+      carry[n] = fmaf(D.run_decay(sd, n), carry[n], end0);
+    }
+  }
+}
+
+// launch_biscan over P concurrent segments per sequence (L % P == 0).  state: float [S*P*2*E*16], sumd: float [S*P*2*E].
+template <typename T, bool PRECISE>
+inline cudaError_t launch_biscan_time_parallel(const T* u_f, const T* delta_f, const T* bc_f, const T* u_r, const T* delta_r,
+                                               const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
+                                               const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
+                                               const float* D_r, const float* bias_r, T* y, int S, int L, int E, int P,
+                                               float* state, float* sumd, cudaStream_t stream) {
+  if (P < 2 || L % P) return cudaErrorInvalidValue;
+  const int Lseg = L / P;
+  dim3 grid((E + kScanCH - 1) / kScanCH, S * P);
+  scan_segment_state_kernel<T, PRECISE><<<grid, kScanThreads, 0, stream>>>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, A_f,
+                                                                           bias_f, A_r, bias_r, state, sumd, Lseg, E);
+  const long long n = static_cast<long long>(S) * 2 * E;
+  scan_segment_carry_kernel<PRECISE><<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(A_f, A_r, state, sumd, S, P, E);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_biscan<T, PRECISE, false>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, bias_f, A_r, D_r,
+                                          bias_r, y, S * P, Lseg, E, stream, nullptr, nullptr, state);
 }
 
 }  // namespace pcad

@@ -29,6 +29,8 @@
 // and the BiMamba "add" of the two directions, in one pass: out = rms(y_f silu(z)) w_f + rms(y_r silu(z)) w_r.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace pcad {
@@ -87,6 +89,15 @@ ssd_scan_seq_kernel(const T* __restrict__ xbc_f, const T* __restrict__ xbc_r, lo
       }
       y[(row0 + pos) * E + h * kSsdP + p] = ActT<T>::from_f(acc);
     }
+  }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
 
@@ -150,6 +161,80 @@ gated_norm_sum_kernel(const T* __restrict__ y_f, const T* __restrict__ y_r, cons
   }
 }
 
+// bf16 variant with the gate cached.  The generic kernel above is MUFU-bound in bf16 (ncu: XU pipe 82 %: SiLU = ex2 + rcp per
+// element, evaluated in both passes) while its second pass already hits L2 (DRAM reads = one pass).  Here SiLU(z) is evaluated
+// once and parked as fp16 in registers (CH 16-byte vectors per lane, E <= 256 CH; 2^-11 relative, below the bf16 rounding of
+// the output; the statistics use the un-rounded fp32 value); y_f / y_r are re-read in the second pass (L2).  Keeping all
+// three tensors in registers instead (one DRAM/L2 pass, 126-230 registers) measured slower: 1.0 vs 0.71 ms per layer at
+// E = 1536 -- too few warps left to overlap the loads with the arithmetic.
+template <int CH>
+__global__ void __launch_bounds__(256)
+gated_norm_sum_regs_kernel(const bf16* __restrict__ y_f, const bf16* __restrict__ y_r, const bf16* __restrict__ z, long long ldz,
+                           const float* __restrict__ w_f, const float* __restrict__ w_r, bf16* __restrict__ out, long long rows,
+                           int E, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* yf = y_f + row * E;
+  const bf16* yr = y_r + row * E;
+  const bf16* zz = z + row * ldz;
+  uint4 rg[CH];
+  float ssf = 0.f, ssr = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int j = (c * 32 + lane) * 8;
+    rg[c] = make_uint4(0u, 0u, 0u, 0u);
+    if (j >= E) continue;
+    float a[8], b[8], g[8];
+    unpack8(*reinterpret_cast<const uint4*>(yf + j), a);
+    unpack8(*reinterpret_cast<const uint4*>(yr + j), b);
+    unpack8(*reinterpret_cast<const uint4*>(zz + j), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      g[k] = silu<false>(g[k]);
+      const float af = a[k] * g[k], ar = b[k] * g[k];
+      ssf = fmaf(af, af, ssf);
+      ssr = fmaf(ar, ar, ssr);
+    }
+    __half2 h0 = __floats2half2_rn(g[0], g[1]), h1 = __floats2half2_rn(g[2], g[3]);
+    __half2 h2 = __floats2half2_rn(g[4], g[5]), h3 = __floats2half2_rn(g[6], g[7]);
+    rg[c] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2),
+                       *reinterpret_cast<uint32_t*>(&h3));
+  }
+  ssf = warp_sum(ssf);
+  ssr = warp_sum(ssr);
+  const float rf = rsqrtf(ssf / static_cast<float>(E) + eps), rr = rsqrtf(ssr / static_cast<float>(E) + eps);
+  bf16* o = out + row * E;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int j = (c * 32 + lane) * 8;
+    if (j >= E) continue;
+    float a[8], b[8], g[8], res[8];
+    unpack8(*reinterpret_cast<const uint4*>(yf + j), a);
+    unpack8(*reinterpret_cast<const uint4*>(yr + j), b);
+    {
+      const uint32_t w[4] = {rg[c].x, rg[c].y, rg[c].z, rg[c].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        g[2 * i] = f.x;
+        g[2 * i + 1] = f.y;
+      }
+    }
+    const float4 f0 = *reinterpret_cast<const float4*>(w_f + j), f1 = *reinterpret_cast<const float4*>(w_f + j + 4);
+    const float4 r0 = *reinterpret_cast<const float4*>(w_r + j), r1 = *reinterpret_cast<const float4*>(w_r + j + 4);
+    const float wf[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+    const float wr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float nf = __bfloat162float(__float2bfloat16_rn(a[k] * g[k] * rf * wf[k]));   // each direction's norm output is bf16
+      const float nr = __bfloat162float(__float2bfloat16_rn(b[k] * g[k] * rr * wr[k]));
+      res[k] = nf + nr;
+    }
+    store16<bf16>(o + j, res);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // chunked SSD on tcgen05
 // ---------------------------------------------------------------------------------------------------------------------
@@ -188,14 +273,6 @@ struct SsdSmem {
   static constexpr int kBytes = kBars + 64;
 };
 
-__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
-  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[2 * i] = __uint_as_float(w[i] << 16);
-    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-  }
-}
 
 // grid (H / 2, S, 2 directions); tm_f / tm_r: 3-D maps [S][L][ld_xbc] of the two directions' conv outputs, box [1][128][64],
 // 128-byte swizzle.  dt_raw [S*L, ld_dt] (column = head).  y_* [S*L, E] un-gated outputs (D skip included).
@@ -206,7 +283,9 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
                     const float* __restrict__ D_r, const float* __restrict__ bias_r, bf16* __restrict__ y_f,
                     bf16* __restrict__ y_r, int L, int E) {
   extern __shared__ uint8_t ssd_smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ssd_smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the swizzled tiles by pointer arithmetic on the array itself, so that the compiler keeps every
+  // access in the shared address space (LDS / STS, not generic LD / ST)
+  uint8_t* sm = ssd_smem_raw + ((1024u - (smem_u32(ssd_smem_raw) & 1023u)) & 1023u);
   float* dts = reinterpret_cast<float*>(sm + SsdSmem::kDts);      // [2][128]  dt (after softplus), 0 for rows past L
   float* cums = reinterpret_cast<float*>(sm + SsdSmem::kCums);    // [2][128]  cumulative dt*A*log2(e) in scan order
   float* wsum = reinterpret_cast<float*>(sm + SsdSmem::kWsum);    // [2][4] warp sums, then tot[2] at +8
@@ -254,6 +333,14 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
   const int head_d = 2 * hp + dh;
   const float A_l2 = Ap[head_d] * kLog2e, bias_d = bp[head_d];
 
+  // raw dt of the chunk about to be processed, fetched one iteration ahead (its global-load latency is off the critical path)
+  auto load_dt = [&](int it_) -> float {
+    if (it_ >= nch) return 0.f;
+    const int c_ = dir ? nch - 1 - it_ : it_;
+    const int pos = c_ * kSsdQ + dtp;
+    return pos < L ? __bfloat162float(dt_raw[(row0 + pos) * ld_dt + head_d]) : -1e30f;   // -1e30: row past the end (dt = 0)
+  };
+  float dt_next = load_dt(0);
   uint32_t tma_phase = 0, mma_phase = 0;
   constexpr uint32_t idesc_g1 = make_idesc_bf16_major(128, 128, 0, 0);
   constexpr uint32_t idesc_g2 = make_idesc_bf16_major(128, 64, 0, 1);
@@ -272,9 +359,9 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
     }
     // ---- dt, log-decay and its cumulative sum in scan order
     {
-      const int pos = p0 + dtp;
-      float dtv = 0.f;
-      if (pos < L) dtv = softplus<true>(__bfloat162float(dt_raw[(row0 + pos) * ld_dt + head_d]) + bias_d);
+      const float raw = dt_next;
+      dt_next = load_dt(it + 1);
+      const float dtv = raw > -1e29f ? softplus<true>(raw + bias_d) : 0.f;
       float v = dtv * A_l2;
       if (dir == 0) {
 #pragma unroll
@@ -324,40 +411,47 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
       {
         uint8_t* mrow = sm + SsdSmem::kM + half * kSsdTile + trow * 128;
         const int tw0 = 32 * (warp & 3);
-#pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
-          const int s0 = 64 * half + 32 * j;
-          const bool masked = dir == 0 ? (s0 > tw0 + 31) : (s0 + 31 < tw0);   // warp-uniform: the whole 32 x 32 block is zero
-          if (masked) {
+        // four 16-column pieces; piece k + 1 is in flight from TMEM while piece k is being computed (a 32-column piece
+        // whose block lies wholly on the masked side of the diagonal -- warp-uniform -- is zero-filled without a load)
+        auto piece_masked = [&](int k) {
+          const int s0 = 64 * half + 32 * (k >> 1);
+          return dir == 0 ? (s0 > tw0 + 31) : (s0 + 31 < tw0);
+        };
+        uint32_t r[2][16];
+        if (!piece_masked(0)) tmem_ld_32x32b_x16(t_lane + 64 * half, r[0]);
+        tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4*>(mrow + (((4 * j + g) ^ (trow & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-            continue;
-          }
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_lane + s0, r);
-          tmem_ld_wait();
+        for (int k = 0; k < 4; ++k) {
+          const int s0 = 64 * half + 16 * k;
+          if (k + 1 < 4 && !piece_masked(k + 1)) tmem_ld_32x32b_x16(t_lane + s0 + 16, r[(k + 1) & 1]);
+          if (piece_masked(k)) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float v[8];
+            for (int g = 0; g < 2; ++g)
+              *reinterpret_cast<uint4*>(mrow + (((2 * k + g) ^ (trow & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          } else {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const float4 cs = *reinterpret_cast<const float4*>(&cums[h * 128 + s0 + 8 * g + 4 * q]);
-              const float4 ds = *reinterpret_cast<const float4*>(&dts[h * 128 + s0 + 8 * g + 4 * q]);
-              const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, dd[4] = {ds.x, ds.y, ds.z, ds.w};
+            for (int g = 0; g < 2; ++g) {
+              float v[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int s = s0 + 8 * g + 4 * q + e;
-                const bool keep = dir == 0 ? (s <= trow) : (s >= trow);
-                const float val = __uint_as_float(r[8 * g + 4 * q + e]) * ex2_approx(cum_t - cc[e]) * dd[e];
-                v[4 * q + e] = keep ? val : 0.f;
+              for (int q = 0; q < 2; ++q) {
+                const float4 cs = *reinterpret_cast<const float4*>(&cums[h * 128 + s0 + 8 * g + 4 * q]);
+                const float4 ds = *reinterpret_cast<const float4*>(&dts[h * 128 + s0 + 8 * g + 4 * q]);
+                const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, dd[4] = {ds.x, ds.y, ds.z, ds.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int s = s0 + 8 * g + 4 * q + e;
+                  const bool keep = dir == 0 ? (s <= trow) : (s >= trow);
+                  const float val = __uint_as_float(r[k & 1][8 * g + 4 * q + e]) * ex2_approx(cum_t - cc[e]) * dd[e];
+                  v[4 * q + e] = keep ? val : 0.f;
+                }
               }
+              uint4 o;
+              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(mrow + (((2 * k + g) ^ (trow & 7)) << 4)) = o;
             }
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(mrow + (((4 * j + g) ^ (trow & 7)) << 4)) = o;
           }
+          tmem_ld_wait();
         }
       }
       // ---- this head's carried state, bf16 K-major [p][n] (written by the threads that hold it)
@@ -396,27 +490,30 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
       tc_fence_after();
       // ---- y = Y + exp(cum_t) Y' + D x  -> global
       {
-        uint32_t yi[32], yo[32];
-        tmem_ld_32x32b_x32(t_lane + 128 + 32 * half, yi);
-        if (it > 0) tmem_ld_32x32b_x32(t_lane + 192 + 32 * half, yo);
-        tmem_ld_wait();
         const float sc = it > 0 ? ex2_approx(cum_t) : 0.f;
         const float Dh = Dp[2 * hp + h];
         const uint8_t* xrow = sm + (h ? SsdSmem::kX1 : SsdSmem::kX0) + trow * 128;
         const int pos = p0 + trow;
         bf16* yp = yout + (row0 + pos) * E + (2 * hp + h) * kSsdP + 32 * half;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float xv[8];
-          unpack8(*reinterpret_cast<const uint4*>(xrow + (((4 * half + g) ^ (trow & 7)) << 4)), xv);
-          float o[8];
+        for (int k = 0; k < 2; ++k) {          // two 16-column pieces (register pressure: the state rows stay live)
+          uint32_t yi[16], yo[16];
+          tmem_ld_32x32b_x16(t_lane + 128 + 32 * half + 16 * k, yi);
+          if (it > 0) tmem_ld_32x32b_x16(t_lane + 192 + 32 * half + 16 * k, yo);
+          tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float v = __uint_as_float(yi[8 * g + e]);
-            if (it > 0) v = fmaf(sc, __uint_as_float(yo[8 * g + e]), v);
-            o[e] = fmaf(Dh, xv[e], v);
+          for (int g = 0; g < 2; ++g) {
+            float xv[8];
+            unpack8(*reinterpret_cast<const uint4*>(xrow + (((4 * half + 2 * k + g) ^ (trow & 7)) << 4)), xv);
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float v = __uint_as_float(yi[8 * g + e]);
+              if (it > 0) v = fmaf(sc, __uint_as_float(yo[8 * g + e]), v);
+              o[e] = fmaf(Dh, xv[e], v);
+            }
+            if (pos < L) store16<bf16>(yp + 16 * k + 8 * g, o);
           }
-          if (pos < L) store16<bf16>(yp + 8 * g, o);
         }
       }
       tc_fence_before();

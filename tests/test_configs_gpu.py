@@ -238,3 +238,27 @@ def test_unmasked_probs_long_context_matches_oracle(cuda_device):
     lg, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
     want = torch.softmax(lg[..., 3:7].float(), dim=-1).numpy()
     assert got.shape == (N, L, 4) and np.allclose(got, want, rtol=2e-4, atol=1e-6)
+
+
+def test_low_batch_long_context_uses_time_parallel_scan(cuda_device, monkeypatch):
+    """B = 1, L = 8192: the forward cuts every sequence into concurrent segments (time-parallel scan) because the sequential
+    scan's grid would leave the GPU idle.  fp32 logits still match the oracle to 1e-4; the bf16 forward agrees with the
+    sequential-scan build of the same engine (PCAD_NO_TIME_PARALLEL=1) and launches two more kernels per layer."""
+    from plantcaduceus_b200.modeling import CaduceusForMaskedLM
+    cfg = CaduceusConfig(d_model=128, n_layer=2)
+    sd = random_init_state_dict(cfg, seed=51)
+    L = 8192
+    g = torch.Generator().manual_seed(7)
+    ids = torch.randint(3, 7, (1, L), generator=g)
+    want, _ = O.caduceus_forward(sd, cfg, ids, dtype=torch.float32)
+    m32 = CaduceusForMaskedLM.from_pretrained(sd, config=cfg, torch_dtype=torch.float32).to(cuda_device)
+    got32 = m32(input_ids=ids.to(cuda_device)).logits.cpu()
+    assert ((got32 - want).abs().max() / want.abs().max()).item() <= 1e-4
+    par = CaduceusForMaskedLM.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    a = par(input_ids=ids.to(cuda_device)).logits.cpu()
+    monkeypatch.setenv("PCAD_NO_TIME_PARALLEL", "1")
+    seq = CaduceusForMaskedLM.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    b = seq(input_ids=ids.to(cuda_device)).logits.cpu()
+    assert par.launch_count() == seq.launch_count() + 2 * cfg.n_layer
+    assert (a - b).abs().max().item() <= 1e-2
+    assert (a - want).abs().max().item() <= max(2e-2, 1.5 * (b - want).abs().max().item())

@@ -285,3 +285,39 @@ def test_two_devices_in_one_process(Model, cuda_device):
         m = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(dev)
         outs.append(m(input_ids=ids.to(dev)).logits.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_small_batch_cuda_graph_replay_is_bit_identical(Model, cuda_device, monkeypatch):
+    """Small score-only forwards are launch-bound (~8 launches per layer of a few microseconds each); from the third call with
+    a shape they are replayed from a CUDA graph captured on the second.  Same bits as eager launches, same launch accounting,
+    and a change of shape / tokenizer in between does not replay a stale graph."""
+    cfg = CaduceusConfig(d_model=256, n_layer=4)
+    sd = random_init_state_dict(cfg, seed=21)
+    rng = np.random.default_rng(4)
+    batches = [torch.from_numpy(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=(3, 512))).pin_memory() for _ in range(5)]
+    other = torch.from_numpy(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=(2, 300))).pin_memory()
+    monkeypatch.setenv("PCAD_NO_GRAPH", "1")
+    eager = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    want = [eager.score_windows_host(b, 255).clone() for b in batches]
+    want_other = eager.score_windows_host(other, 100).clone()
+    n_eager = eager.launch_count()
+    monkeypatch.delenv("PCAD_NO_GRAPH")
+    graphed = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+    got = []
+    for k, b in enumerate(batches):
+        got.append(graphed.score_windows_host(b, 255).clone())
+        if k == 2:   # a different shape and position in between: its own (eager) path, the cached graph stays valid
+            assert torch.equal(graphed.score_windows_host(other, 100), want_other)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert graphed.launch_count() == n_eager
+    # device entry point shares the graphs
+    dev_out = graphed.score_windows_device(batches[0].to(cuda_device), 255).cpu()
+    assert torch.equal(dev_out, want[0])
+    # a new tokenizer invalidates the captured launches (mask id / column selection are baked in)
+    vocab = {"[PAD]": 0, "[UNK]": 1, "[MASK]": 2, "t": 3, "a": 4, "g": 5, "c": 6}
+    tok = CharDNATokenizer(vocab=vocab)
+    graphed.set_tokenizer(tok)
+    eager.set_tokenizer(tok)
+    for _ in range(3):
+        assert torch.equal(graphed.score_windows_host(batches[1], 255), eager.score_windows_host(batches[1], 255))

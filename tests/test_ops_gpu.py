@@ -264,3 +264,48 @@ def test_biscan_with_in_kernel_dt_proj(lib, cuda_device, S, L, E, R):
     # argument checks: ldbc >= 64
     assert lib.pcad_op_biscan_dt(ptr(u[0]), ptr(dbc[0]), ptr(u[1]), ptr(dbc[1]), 48, R, ptr(Wp[0]), ptr(Wp[1]), z_ptr, 2 * E,
                                  ptr(A[0]), ptr(D[0]), ptr(bias[0]), ptr(A[1]), ptr(D[1]), ptr(bias[1]), ptr(y), S, L, E, stream()) != 0
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("S,L,E,R,P", [(1, 512, 128, 8, 4), (2, 1024, 256, 24, 8), (1, 96, 128, 8, 2), (3, 320, 200, 8, 5), (1, 8192, 128, 8, 16)])
+def test_biscan_time_parallel_matches_sequential(lib, cuda_device, dtype, S, L, E, R, P):
+    """pcad_op_biscan_segmented (P concurrent segments per sequence: zero-state scans -> carry combine -> scans from the carried
+    states) against the sequential pcad_op_biscan on the same inputs: the recurrence is linear in the state, so the two differ
+    only by fp32 rounding of the carry (fp32: 2e-5 of the output scale; bf16 outputs: the odd 1-ulp flip)."""
+    N = 16
+    td = torch.float32 if dtype == F32 else torch.bfloat16
+    g = torch.Generator().manual_seed(S * 100 + L + P)
+    RP = (R + 2 * N + 15) // 16 * 16
+    mk = lambda *shape: torch.randn(*shape, generator=g)
+    dev = lambda t: t.to(cuda_device).contiguous()
+    u = [dev(mk(S * L, E).to(td)) for _ in range(2)]
+    dl = [dev((mk(S * L, E) * 0.5).to(td)) for _ in range(2)]
+    bc = [dev(mk(S * L, RP).to(td)) for _ in range(2)]
+    xz = dev(mk(S * L, 2 * E).to(td))
+    # slow decays too (|A| dt ~ 1e-3): the carried state matters across every segment
+    A = [dev(-(torch.rand(E, N, generator=g) * 4 + 0.01)) for _ in range(2)]
+    D = [dev(mk(E)) for _ in range(2)]
+    bias = [dev(mk(E) - 4) for _ in range(2)]
+    z_ptr = C.c_void_p(xz.data_ptr() + E * xz.element_size())
+    y_seq = torch.full((S * L, E), float("nan"), device=cuda_device, dtype=td)
+    y_par = torch.full((S * L, E), float("nan"), device=cuda_device, dtype=td)
+    check(lib, lib.pcad_op_biscan(ptr(u[0]), ptr(dl[0]), ptr(bc[0]), ptr(u[1]), ptr(dl[1]), ptr(bc[1]), RP, R, z_ptr, 2 * E,
+                                  ptr(A[0]), ptr(D[0]), ptr(bias[0]), ptr(A[1]), ptr(D[1]), ptr(bias[1]), ptr(y_seq), S, L, E, dtype, stream()))
+    state = torch.full((S * P * 2 * E * 16,), float("nan"), device=cuda_device)
+    sumd = torch.full((S * P * 2 * E,), float("nan"), device=cuda_device)
+    check(lib, lib.pcad_op_biscan_segmented(ptr(u[0]), ptr(dl[0]), ptr(bc[0]), ptr(u[1]), ptr(dl[1]), ptr(bc[1]), RP, R, z_ptr, 2 * E,
+                                            ptr(A[0]), ptr(D[0]), ptr(bias[0]), ptr(A[1]), ptr(D[1]), ptr(bias[1]), ptr(y_par), S, L, E, P,
+                                            ptr(state), ptr(sumd), dtype, stream()))
+    torch.cuda.synchronize()
+    a, b = y_seq.float(), y_par.float()
+    assert not torch.isnan(b).any()
+    scale = a.abs().max().item()
+    if dtype == F32:
+        assert (a - b).abs().max().item() <= 2e-5 * scale + 1e-6
+    else:
+        assert (a - b).abs().max().item() <= 2 ** -7 * scale
+        assert (a == b).float().mean().item() >= 0.98
+    # L not divisible by the segment count is refused
+    assert lib.pcad_op_biscan_segmented(ptr(u[0]), ptr(dl[0]), ptr(bc[0]), ptr(u[1]), ptr(dl[1]), ptr(bc[1]), RP, R, z_ptr, 2 * E,
+                                        ptr(A[0]), ptr(D[0]), ptr(bias[0]), ptr(A[1]), ptr(D[1]), ptr(bias[1]), ptr(y_par), S, L, E, 7,
+                                        ptr(state), ptr(sumd), dtype, stream()) != 0
