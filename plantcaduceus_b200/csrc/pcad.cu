@@ -577,11 +577,13 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
                        st, lw.dir[0].dt_proj_p, lw.dir[1].dt_proj_p);
       else {
         // low batch / long context: cut every sequence into P concurrent segments while the sequential kernel's grid
-        // (E / 64 x S CTAs) would leave resident slots (4 per SM) empty and the segments stay >= 128 steps long
+        // (E / 64 x S CTAs) would leave resident slots (4 per SM) empty and the segments stay >= 512 steps long.  (Measured:
+        // with shorter segments the two extra passes cost more than the parallelism returns -- B = 4, L = 512: 10.9 vs 6.5 ms;
+        // and 512-bp windows, the scoring workload, keep the property that a window scores the same bits alone or in a batch.)
         int P = 1;
         if (h->time_parallel) {
           const long long ctas = static_cast<long long>((E + kScanCH - 1) / kScanCH) * S, slots = 4LL * h->num_sms;
-          while (P < 32 && ctas * P * 2 <= slots && L % (P * 2) == 0 && L / (P * 2) >= 128 &&
+          while (P < 32 && ctas * P * 2 <= slots && L % (P * 2) == 0 && L / (P * 2) >= 512 &&
                  static_cast<size_t>(S) * P * 2 * 2 * E * kScanN * sizeof(float) <= kSegStateBytes)
             P *= 2;
         }

@@ -405,56 +405,59 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
     mma_phase ^= 1;
     tc_fence_after();
 
-    for (int h = 0; h < 2; ++h) {
+    // ---- per-head pieces of the chunk.  Phases (one barrier each): [M_0, S_0] | MMA_0 | [y_0, M_1, S_1] | MMA_1 | [y_1, Xw] |
+    //      MMA_3 | state -- the epilogue of one head shares a phase with the next head's operand build, so the light rows of the
+    //      triangular M build have the (uniform) epilogue to do while the heavy rows finish.
+    // M = G o decay o dt, bf16, K-major swizzled: tile `half` holds columns [64 half, 64 half + 64)
+    auto build_M = [&](int h) {
       const float cum_t = cums[h * 128 + trow];
-      // ---- M = G o decay o dt, bf16, K-major swizzled: tile `half` holds columns [64 half, 64 half + 64)
-      {
-        uint8_t* mrow = sm + SsdSmem::kM + half * kSsdTile + trow * 128;
-        const int tw0 = 32 * (warp & 3);
-        // four 16-column pieces; piece k + 1 is in flight from TMEM while piece k is being computed (a 32-column piece
-        // whose block lies wholly on the masked side of the diagonal -- warp-uniform -- is zero-filled without a load)
-        auto piece_masked = [&](int k) {
-          const int s0 = 64 * half + 32 * (k >> 1);
-          return dir == 0 ? (s0 > tw0 + 31) : (s0 + 31 < tw0);
-        };
-        uint32_t r[2][16];
-        if (!piece_masked(0)) tmem_ld_32x32b_x16(t_lane + 64 * half, r[0]);
-        tmem_ld_wait();
+      uint8_t* mrow = sm + SsdSmem::kM + half * kSsdTile + trow * 128;
+      const int tw0 = 32 * (warp & 3);
+      // four 16-column pieces; piece k + 1 is in flight from TMEM while piece k is being computed (a 32-column piece
+      // whose block lies wholly on the masked side of the diagonal -- warp-uniform -- is zero-filled without a load)
+      auto piece_masked = [&](int k) {
+        const int s0 = 64 * half + 32 * (k >> 1);
+        return dir == 0 ? (s0 > tw0 + 31) : (s0 + 31 < tw0);
+      };
+      uint32_t r[2][16];
+      if (!piece_masked(0)) tmem_ld_32x32b_x16(t_lane + 64 * half, r[0]);
+      tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int s0 = 64 * half + 16 * k;
-          if (k + 1 < 4 && !piece_masked(k + 1)) tmem_ld_32x32b_x16(t_lane + s0 + 16, r[(k + 1) & 1]);
-          if (piece_masked(k)) {
+      for (int k = 0; k < 4; ++k) {
+        const int s0 = 64 * half + 16 * k;
+        if (k + 1 < 4 && !piece_masked(k + 1)) tmem_ld_32x32b_x16(t_lane + s0 + 16, r[(k + 1) & 1]);
+        if (piece_masked(k)) {
 #pragma unroll
-            for (int g = 0; g < 2; ++g)
-              *reinterpret_cast<uint4*>(mrow + (((2 * k + g) ^ (trow & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-          } else {
+          for (int g = 0; g < 2; ++g)
+            *reinterpret_cast<uint4*>(mrow + (((2 * k + g) ^ (trow & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        } else {
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              float v[8];
+          for (int g = 0; g < 2; ++g) {
+            float v[8];
 #pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const float4 cs = *reinterpret_cast<const float4*>(&cums[h * 128 + s0 + 8 * g + 4 * q]);
-                const float4 ds = *reinterpret_cast<const float4*>(&dts[h * 128 + s0 + 8 * g + 4 * q]);
-                const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, dd[4] = {ds.x, ds.y, ds.z, ds.w};
+            for (int q = 0; q < 2; ++q) {
+              const float4 cs = *reinterpret_cast<const float4*>(&cums[h * 128 + s0 + 8 * g + 4 * q]);
+              const float4 ds = *reinterpret_cast<const float4*>(&dts[h * 128 + s0 + 8 * g + 4 * q]);
+              const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, dd[4] = {ds.x, ds.y, ds.z, ds.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int s = s0 + 8 * g + 4 * q + e;
-                  const bool keep = dir == 0 ? (s <= trow) : (s >= trow);
-                  const float val = __uint_as_float(r[k & 1][8 * g + 4 * q + e]) * ex2_approx(cum_t - cc[e]) * dd[e];
-                  v[4 * q + e] = keep ? val : 0.f;
-                }
+              for (int e = 0; e < 4; ++e) {
+                const int s = s0 + 8 * g + 4 * q + e;
+                const bool keep = dir == 0 ? (s <= trow) : (s >= trow);
+                const float val = __uint_as_float(r[k & 1][8 * g + 4 * q + e]) * ex2_approx(cum_t - cc[e]) * dd[e];
+                v[4 * q + e] = keep ? val : 0.f;
               }
-              uint4 o;
-              o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-              o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(mrow + (((2 * k + g) ^ (trow & 7)) << 4)) = o;
             }
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(mrow + (((2 * k + g) ^ (trow & 7)) << 4)) = o;
           }
-          tmem_ld_wait();
         }
+        tmem_ld_wait();
       }
-      // ---- this head's carried state, bf16 K-major [p][n] (written by the threads that hold it)
+    };
+    // this head's carried state, bf16 K-major [p][n] (written by the threads that hold it)
+    auto write_S = [&](int h) {
       if (it > 0 && (trow >> 6) == h) {
         uint8_t* srow = sm + SsdSmem::kS + (trow & 63) * 128;
 #pragma unroll
@@ -465,10 +468,9 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
           *reinterpret_cast<uint4*>(srow + (((4 * half + g) ^ (trow & 7)) << 4)) = o;
         }
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      // ---- GEMM2: Y = M X_h;  GEMM4: Y' = C S^T
+    };
+    // GEMM2: Y = M X_h;  GEMM4: Y' = C S^T;  then every thread waits for both
+    auto mma_head = [&](int h) {
       if (tid == 0) {
         tc_fence_after();
         const uint32_t xa = sm_addr + (h ? SsdSmem::kX1 : SsdSmem::kX0);
@@ -488,40 +490,40 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
       mbar_wait_or_trap(mma_bar, mma_phase);
       mma_phase ^= 1;
       tc_fence_after();
-      // ---- y = Y + exp(cum_t) Y' + D x  -> global
-      {
-        const float sc = it > 0 ? ex2_approx(cum_t) : 0.f;
-        const float Dh = Dp[2 * hp + h];
-        const uint8_t* xrow = sm + (h ? SsdSmem::kX1 : SsdSmem::kX0) + trow * 128;
-        const int pos = p0 + trow;
-        bf16* yp = yout + (row0 + pos) * E + (2 * hp + h) * kSsdP + 32 * half;
+    };
+    // y = Y + exp(cum_t) Y' + D x  -> global
+    auto epilogue = [&](int h) {
+      const float cum_t = cums[h * 128 + trow];
+      const float sc = it > 0 ? ex2_approx(cum_t) : 0.f;
+      const float Dh = Dp[2 * hp + h];
+      const uint8_t* xrow = sm + (h ? SsdSmem::kX1 : SsdSmem::kX0) + trow * 128;
+      const int pos = p0 + trow;
+      bf16* yp = yout + (row0 + pos) * E + (2 * hp + h) * kSsdP + 32 * half;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {          // two 16-column pieces (register pressure: the state rows stay live)
-          uint32_t yi[16], yo[16];
-          tmem_ld_32x32b_x16(t_lane + 128 + 32 * half + 16 * k, yi);
-          if (it > 0) tmem_ld_32x32b_x16(t_lane + 192 + 32 * half + 16 * k, yo);
-          tmem_ld_wait();
+      for (int k = 0; k < 2; ++k) {          // two 16-column pieces (register pressure: the state rows stay live)
+        uint32_t yi[16], yo[16];
+        tmem_ld_32x32b_x16(t_lane + 128 + 32 * half + 16 * k, yi);
+        if (it > 0) tmem_ld_32x32b_x16(t_lane + 192 + 32 * half + 16 * k, yo);
+        tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            float xv[8];
-            unpack8(*reinterpret_cast<const uint4*>(xrow + (((4 * half + 2 * k + g) ^ (trow & 7)) << 4)), xv);
-            float o[8];
+        for (int g = 0; g < 2; ++g) {
+          float xv[8];
+          unpack8(*reinterpret_cast<const uint4*>(xrow + (((4 * half + 2 * k + g) ^ (trow & 7)) << 4)), xv);
+          float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float v = __uint_as_float(yi[8 * g + e]);
-              if (it > 0) v = fmaf(sc, __uint_as_float(yo[8 * g + e]), v);
-              o[e] = fmaf(Dh, xv[e], v);
-            }
-            if (pos < L) store16<bf16>(yp + 16 * k + 8 * g, o);
+          for (int e = 0; e < 8; ++e) {
+            float v = __uint_as_float(yi[8 * g + e]);
+            if (it > 0) v = fmaf(sc, __uint_as_float(yo[8 * g + e]), v);
+            o[e] = fmaf(Dh, xv[e], v);
           }
+          if (pos < L) store16<bf16>(yp + 16 * k + 8 * g, o);
         }
       }
-      tc_fence_before();
-      __syncthreads();   // Y / Y' accumulators, the M tiles and the S tile are free again
-    }
+    };
+    const bool more = it + 1 < nch;
 
-    if (it + 1 < nch) {
-      // ---- X w for both heads (into the M tiles), w_s = exp(cum_end - cum_s) dt_s
+    // X w for both heads (into the M tiles), w_s = exp(cum_end - cum_s) dt_s
+    auto build_Xw = [&]() {
       for (int idx = tid; idx < 2 * kSsdQ * 8; idx += kSsdThreads) {
         const int hh = idx >> 10, r = (idx >> 3) & 127, cp = idx & 7;
         const float w = ex2_approx(wsum[8 + hh] - cums[hh * 128 + r]) * dts[hh * 128 + r];
@@ -534,8 +536,23 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
         o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
         *reinterpret_cast<uint4*>(sm + SsdSmem::kM + hh * kSsdTile + r * 128 + cp * 16) = o;
       }
+    };
+    // one copy of every piece (runtime phase index): phase 0 [M_0 S_0] MMA_0, phase 1 [y_0 M_1 S_1] MMA_1, phase 2 [y_1 Xw]
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ++ph) {
+      if (ph > 0) epilogue(ph - 1);   // the previous head's MMAs have completed: its M tiles and the S tile are free as well
+      if (ph < 2) {
+        build_M(ph);
+        write_S(ph);
+      } else if (more) {
+        build_Xw();
+      }
       fence_proxy_async_smem();
-      __syncthreads();
+      tc_fence_before();
+      __syncthreads();                // every thread has read the previous head's Y / Y' before the next MMAs overwrite them
+      if (ph < 2) mma_head(ph);
+    }
+    if (more) {
       // ---- GEMM3: S_c[(h, p), n] = sum_s Xw[s, (h, p)] B[s, n]
       if (tid == 0) {
         tc_fence_after();
