@@ -15,6 +15,8 @@
 // in scan order and all tiles staged by TMA with the 128-byte swizzle:
 //   GEMM1  G = C B^T                       128 x 128 x 64   (A, B K-major)                        -> TMEM
 //   per head:  M[t,s] = G[t,s] exp(cum_t - cum_s) dt_s  for s not after t (else 0), bf16, written K-major into smem
+//              (32 x 32 blocks off the diagonal: exp(cum_t - r) exp(r - cum_s) with r the block edge, both factors <= 1, so the
+//              per-element exponential is two multiplies there; blocks on the masked side are zero-filled)
 //   GEMM2  Y  = M X                         128 x 64 x 128   (B operand = the x tile as loaded: MN-major)
 //   GEMM4  Y' = C S_prev^T                  128 x 64 x 64    (S_prev rounded to bf16 in smem, K-major)
 //          y_t = Y + exp(cum_t) Y' + D x_t  -> global (bf16)
@@ -268,7 +270,8 @@ struct SsdSmem {
   static constexpr int kSmall = kS + 8192;
   static constexpr int kDts = kSmall;                      // float [2][128]
   static constexpr int kCums = kDts + 1024;                // float [2][128]
-  static constexpr int kWsum = kCums + 1024;               // float [2][4] + tot [2]
+  static constexpr int kColf = kCums + 1024;               // float [2][4][128]: column factors of the off-diagonal blocks
+  static constexpr int kWsum = kColf + 4096;               // float [2][4] + tot [2]
   static constexpr int kBars = kWsum + 64;                 // 2 mbarriers + tmem ptr
   static constexpr int kBytes = kBars + 64;
 };
@@ -288,6 +291,7 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
   uint8_t* sm = ssd_smem_raw + ((1024u - (smem_u32(ssd_smem_raw) & 1023u)) & 1023u);
   float* dts = reinterpret_cast<float*>(sm + SsdSmem::kDts);      // [2][128]  dt (after softplus), 0 for rows past L
   float* cums = reinterpret_cast<float*>(sm + SsdSmem::kCums);    // [2][128]  cumulative dt*A*log2(e) in scan order
+  float* colf = reinterpret_cast<float*>(sm + SsdSmem::kColf);    // [2][4][128] (head, row block I, column s): 2^(r_I - cum_s) dt_s
   float* wsum = reinterpret_cast<float*>(sm + SsdSmem::kWsum);    // [2][4] warp sums, then tot[2] at +8
   uint64_t* tma_bar = reinterpret_cast<uint64_t*>(sm + SsdSmem::kBars);
   uint64_t* mma_bar = tma_bar + 1;
@@ -387,8 +391,23 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
         const float s = wsum[dh * 4 + w];
         if (dir == 0 ? (w < wq) : (w > wq)) off += s;
       }
-      cums[dh * 128 + dtp] = v + off;
+      const float cum_s = v + off;
+      cums[dh * 128 + dtp] = cum_s;
       if (dtp == 0) wsum[8 + dh] = wsum[dh * 4] + wsum[dh * 4 + 1] + wsum[dh * 4 + 2] + wsum[dh * 4 + 3];
+      // Column factors for the 32 x 32 blocks that lie wholly on the unmasked side of the diagonal.  With r_I the cumulative
+      // log-decay at the edge of row block I that faces this column (= a sum of whole-warp totals), the decay from s to a row t
+      // of block I splits as 2^(cum_t - r_I) 2^(r_I - cum_s) with BOTH exponents <= 0: no overflow however fast the state
+      // forgets, and the per-element exponential of those blocks becomes two multiplies in build_M.
+      {
+        float r = 0.f;   // r_I, accumulated over the row blocks in scan order
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          const int I = dir == 0 ? k : 3 - k;                 // row blocks that come after this column's block in scan order
+          r += wsum[dh * 4 + (dir == 0 ? k - 1 : 4 - k)];     // fwd: r_I = sum of warps < I;  rev: sum of warps > I
+          const bool needed = dir == 0 ? (wq < I) : (wq > I);
+          if (needed) colf[(dh * 4 + I) * 128 + dtp] = ex2_approx(r - cum_s) * dtv;
+        }
+      }
     }
     __syncthreads();
     // ---- GEMM1: G = C B^T
@@ -408,28 +427,58 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
     // ---- per-head pieces of the chunk.  Phases (one barrier each): [M_0, S_0] | MMA_0 | [y_0, M_1, S_1] | MMA_1 | [y_1, Xw] |
     //      MMA_3 | state -- the epilogue of one head shares a phase with the next head's operand build, so the light rows of the
     //      triangular M build have the (uniform) epilogue to do while the heavy rows finish.
-    // M = G o decay o dt, bf16, K-major swizzled: tile `half` holds columns [64 half, 64 half + 64)
+    // M = G o decay o dt, bf16, K-major swizzled (tile = columns / 64).  A thread owns row `trow` and the four 16-column
+    // pieces {half, half + 2, half + 4, half + 6}: interleaved, so the two warps that share a row block split its diagonal
+    // block.  A piece lies in column block J = piece / 2; against the row block I (warp-uniform):
+    //   masked side of the diagonal -> zero-filled, no TMEM load;
+    //   J == I                      -> per element 2^(cum_t - cum_s) dt_s under the triangular mask;
+    //   unmasked side               -> G[t,s] * rowf_t * colf_I[s]: two multiplies per element (see the dt phase).
+    // Piece k + 1 is in flight from TMEM while piece k is being computed.
     auto build_M = [&](int h) {
       const float cum_t = cums[h * 128 + trow];
-      uint8_t* mrow = sm + SsdSmem::kM + half * kSsdTile + trow * 128;
-      const int tw0 = 32 * (warp & 3);
-      // four 16-column pieces; piece k + 1 is in flight from TMEM while piece k is being computed (a 32-column piece
-      // whose block lies wholly on the masked side of the diagonal -- warp-uniform -- is zero-filled without a load)
-      auto piece_masked = [&](int k) {
-        const int s0 = 64 * half + 32 * (k >> 1);
-        return dir == 0 ? (s0 > tw0 + 31) : (s0 + 31 < tw0);
+      const int I = warp & 3;
+      uint8_t* mbase = sm + SsdSmem::kM + trow * 128;
+      // r_I (edge of this row block facing the unmasked columns) from the whole-warp totals, and this row's factor
+      float rI = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (dir == 0 ? (w < I) : (w > I)) rI += wsum[h * 4 + w];
+      const float rowf = ex2_approx(cum_t - rI);
+      const float* cf = colf + (h * 4 + I) * 128;
+      auto kind = [&](int kk) {   // 0 masked, 1 diagonal, 2 full
+        const int J = (2 * kk + half) >> 1;
+        if (J == I) return 1;
+        return (dir == 0 ? (J < I) : (J > I)) ? 2 : 0;
       };
       uint32_t r[2][16];
-      if (!piece_masked(0)) tmem_ld_32x32b_x16(t_lane + 64 * half, r[0]);
+      if (kind(0)) tmem_ld_32x32b_x16(t_lane + 16 * half, r[0]);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int s0 = 64 * half + 16 * k;
-        if (k + 1 < 4 && !piece_masked(k + 1)) tmem_ld_32x32b_x16(t_lane + s0 + 16, r[(k + 1) & 1]);
-        if (piece_masked(k)) {
+      for (int kk = 0; kk < 4; ++kk) {
+        const int piece = 2 * kk + half;
+        const int s0 = 16 * piece;
+        uint8_t* mrow = mbase + (piece >> 2) * kSsdTile;
+        const int c0 = 2 * (piece & 3);                       // first 16-byte chunk of the piece inside its tile row
+        if (kk + 1 < 4 && kind(kk + 1)) tmem_ld_32x32b_x16(t_lane + s0 + 32, r[(kk + 1) & 1]);
+        const int kd = kind(kk);
+        if (kd == 0) {
 #pragma unroll
           for (int g = 0; g < 2; ++g)
-            *reinterpret_cast<uint4*>(mrow + (((2 * k + g) ^ (trow & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(mrow + (((c0 + g) ^ (trow & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        } else if (kd == 2) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const float4 f0 = *reinterpret_cast<const float4*>(&cf[s0 + 8 * g]);
+            const float4 f1 = *reinterpret_cast<const float4*>(&cf[s0 + 8 * g + 4]);
+            const float ff[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[kk & 1][8 * g + e]) * rowf * ff[e];
+            uint4 o;
+            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(mrow + (((c0 + g) ^ (trow & 7)) << 4)) = o;
+          }
         } else {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -443,14 +492,14 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
               for (int e = 0; e < 4; ++e) {
                 const int s = s0 + 8 * g + 4 * q + e;
                 const bool keep = dir == 0 ? (s <= trow) : (s >= trow);
-                const float val = __uint_as_float(r[k & 1][8 * g + 4 * q + e]) * ex2_approx(cum_t - cc[e]) * dd[e];
+                const float val = __uint_as_float(r[kk & 1][8 * g + 4 * q + e]) * ex2_approx(cum_t - cc[e]) * dd[e];
                 v[4 * q + e] = keep ? val : 0.f;
               }
             }
             uint4 o;
             o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
             o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(mrow + (((2 * k + g) ^ (trow & 7)) << 4)) = o;
+            *reinterpret_cast<uint4*>(mrow + (((c0 + g) ^ (trow & 7)) << 4)) = o;
           }
         }
         tmem_ld_wait();

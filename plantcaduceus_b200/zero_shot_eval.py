@@ -51,12 +51,22 @@ def masked_probs(model, tokenizer, sequences: Sequence[str], mask_idx: Sequence[
     return out
 
 
-def unmasked_probs(model, tokenizer, sequences: Sequence[str], batch_size: int = 16) -> np.ndarray:
-    """Per-position probabilities over A,C,G,T for each (unmasked) sequence: float32 ``[N, L, 4]`` (:143-178)."""
+def unmasked_probs(model, tokenizer, sequences: Sequence[str], batch_size: int = 16, on_device: bool = False):
+    """Per-position probabilities over A,C,G,T for each (unmasked) sequence: float32 ``[N, L, 4]`` (:143-178).
+    ``on_device=True`` returns a torch tensor that stays on the model's device (at L = 8192 the ``[N, L, 4]`` array is what
+    crosses PCIe otherwise; ``sv_llr_boundary`` accepts it and gathers its 2 * flanking values per row there)."""
     ascii_mat = _ascii_matrix(tokenizer, sequences)
     n, L = ascii_mat.shape
     v = tokenizer.get_vocab()
     idxs = [v[c] for c in "acgt"]
+    if on_device:
+        out_dev = torch.zeros((n, L, 4), dtype=torch.float32, device=model.device)
+        sel = torch.tensor(idxs, device=model.device)
+        for s in range(0, n, batch_size):
+            ids = torch.from_numpy(tokenizer.encode_bytes(ascii_mat[s:s + batch_size]).astype(np.int64))
+            logits = model(input_ids=ids.to(model.device)).logits
+            out_dev[s:s + len(ids)] = torch.softmax(logits.index_select(-1, sel).float(), dim=-1)
+        return out_dev
     out = np.zeros((n, L, 4), dtype=np.float32)
     for s in range(0, n, batch_size):
         ids = torch.from_numpy(tokenizer.encode_bytes(ascii_mat[s:s + batch_size]).astype(np.int64))
@@ -75,6 +85,8 @@ def sv_llr_boundary(left: Sequence[int], right: Sequence[int], mut_seqs: Sequenc
     n = len(mut_seqs)
     L = ref_probs.shape[1]
     c = L // 2
+    if isinstance(ref_probs, torch.Tensor) or isinstance(mut_probs, torch.Tensor):
+        return _sv_llr_boundary_device(left, right, mut_seqs, ref_probs, mut_probs, flanking)
     k = np.arange(flanking)
     left = np.asarray(left, dtype=np.int64)
     right = np.asarray(right, dtype=np.int64)
@@ -92,6 +104,33 @@ def sv_llr_boundary(left: Sequence[int], right: Sequence[int], mut_seqs: Sequenc
     m = mut_probs[rows, mut_pos, ch]
     vals = np.where(valid, np.log(np.maximum(m, 1e-12) / np.maximum(r, 1e-12)), 0.0)
     return -vals.mean(axis=1)
+
+
+def _sv_llr_boundary_device(left, right, mut_seqs, ref_probs, mut_probs, flanking: int) -> np.ndarray:
+    """``sv_llr_boundary`` with the probability tensors resident on the device: the 2 * flanking (position, channel) pairs of
+    every row are gathered there and only the ``[n]`` scores come back."""
+    dev = ref_probs.device if isinstance(ref_probs, torch.Tensor) else mut_probs.device
+    ref_probs = torch.as_tensor(ref_probs, device=dev)
+    mut_probs = torch.as_tensor(mut_probs, device=dev)
+    n, L = len(mut_seqs), ref_probs.shape[1]
+    c = L // 2
+    k = torch.arange(flanking, device=dev)
+    left_t = torch.as_tensor(np.asarray(left, dtype=np.int64), device=dev)
+    right_t = torch.as_tensor(np.asarray(right, dtype=np.int64), device=dev)
+    ref_pos = torch.cat([(left_t[:, None] - 1) - (flanking - 1) + k[None, :] - 1, (right_t[:, None] + 1) + k[None, :] - 1], dim=1)
+    mut_pos = torch.cat([c - flanking + k, c + k])[None, :].expand(n, -1)
+    centre = np.array([list(str(s)[c - flanking:c + flanking].upper().ljust(2 * flanking, "N")) for s in mut_seqs])
+    chan = np.full(centre.shape, -1, dtype=np.int64)
+    for j, b in enumerate(NUCLEOTIDES):
+        chan[centre == b] = j
+    chan_t = torch.as_tensor(chan, device=dev)
+    valid = chan_t >= 0
+    ch = torch.where(valid, chan_t, torch.zeros_like(chan_t))
+    rows = torch.arange(n, device=dev)[:, None].expand(-1, 2 * flanking)
+    r = ref_probs[rows, ref_pos, ch]
+    m = mut_probs[rows, mut_pos, ch]
+    vals = torch.where(valid, torch.log(torch.clamp(m, min=1e-12) / torch.clamp(r, min=1e-12)), torch.zeros_like(m))
+    return (-vals.mean(dim=1)).cpu().numpy()
 
 
 def compute_true_tokens_from_seq(sequences: Sequence[str], positions: List[int]) -> np.ndarray:

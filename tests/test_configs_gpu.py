@@ -116,6 +116,11 @@ def test_zero_shot_eval_helpers_match_reference_formulas(cuda_device):
                     vals.append(0.0)
         want_sv[i] = -float(np.mean(vals))
     assert np.allclose(got_sv, want_sv, rtol=1e-5, atol=1e-7)
+    # the same with the probabilities left on the device: only the [N] scores cross PCIe
+    up_dev = zse.unmasked_probs(model, tok, seqs, batch_size=3, on_device=True)
+    assert up_dev.is_cuda and np.allclose(up_dev.cpu().numpy(), up, rtol=1e-6, atol=1e-7)
+    got_dev = zse.sv_llr_boundary(left, right, mut, up_dev, torch.from_numpy(mp).to(cuda_device), flank)
+    assert np.allclose(got_dev, want_sv, rtol=1e-5, atol=1e-6)
 
 
 def test_device_window_extraction_bit_exact_and_genome_scoring(cuda_device):

@@ -3,8 +3,9 @@
 
     python tools/summarize_profiles.py [round_tag]        (default r01)
 
-Needs the ncu CLI (reads .ncu-rep files; no GPU).  Inputs (all optional): gpurun_out/launches_r1.csv (launch list from
-`ncu --metrics gpu__time_duration.sum`), gpurun_out/{scan,gemm,elem}_r1.ncu-rep (`ncu --set full` captures).
+Needs the ncu CLI (reads .ncu-rep files; no GPU).  Inputs (all optional), written by tools/final_suite.sh <tag>:
+gpurun_out/launches_<tag>.csv (launch list from `ncu --metrics gpu__time_duration.sum`) and
+gpurun_out/{scan,gemm,elem,ssd}_<tag>.ncu-rep (`ncu --set full` captures).
 """
 import collections
 import csv
@@ -16,7 +17,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 COMMON = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
           'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
@@ -77,7 +78,7 @@ def dump(rep, out, title, stalls=False):
 
 
 def launches():
-    p = os.path.join(OUT, "launches_r1.csv")
+    p = os.path.join(OUT, f"launches_{TAG}.csv")
     if not os.path.exists(p):
         return
     rows = [r for r in csv.reader(open(p)) if len(r) > 10]
@@ -107,7 +108,7 @@ def launches():
 def main():
     os.makedirs(PROF, exist_ok=True)
     launches()
-    scan = dump("scan_r1.ncu-rep", f"{TAG}_scan_ncu_summary.txt",
+    scan = dump(f"scan_{TAG}.ncu-rep", f"{TAG}_scan_ncu_summary.txt",
                 "ncu --set full --clock-control none --import-source on -k regex:biscan -s 3 -c 1  python bench.py --steps 1 --warmup 1 --cpu-sample 0 --no-clocks\n"
                 "pcad::biscan_kernel<__nv_bfloat16, false, false>  (PlantCaduceus_l32, B=256 x 512 bp: S=512 sequences, E=2048, one launch per layer)\n"
                 "algorithmic bytes per launch 6.543 GB (817.9 MB/window / 32 layers x 256 windows)", stalls=True)
@@ -118,13 +119,21 @@ def main():
         json.dump({"l32": traffic, "source": f"profiles/{TAG}_scan_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch, B=256)"},
                   open(os.path.join(PROF, "scan_traffic.json"), "w"))
         print(open(os.path.join(PROF, f"{TAG}_scan_ncu_summary.txt")).read())
-    dump("gemm_r1.ncu-rep", f"{TAG}_gemm_ncu_summary.txt",
+    dump(f"gemm_{TAG}.ncu-rep", f"{TAG}_gemm_ncu_summary.txt",
          "ncu --set full --clock-control none -k regex:gemm_bf16 -s 8 -c 6 python bench.py --steps 1 --warmup 1 --cpu-sample 0 --no-clocks\n"
          "PlantCaduceus_l32, B=256 (T = 262144 strand-tokens). Launch order within a layer: in_proj<256, row-scale epilogue> [T,1024]x[4096,1024]; "
          "x_proj<96> [T,2048]x[96,2048]; dt_proj<256> [T,64]x[2048,64]; (x_proj, dt_proj again for the reverse direction); "
          "out_proj<256, residual epilogue> [T,2048]x[1024,2048].  UTCHMMA = tcgen05.mma.")
-    dump("elem_r1.ncu-rep", f"{TAG}_conv_norm_ncu_summary.txt",
+    dump(f"elem_{TAG}.ncu-rep", f"{TAG}_conv_norm_ncu_summary.txt",
          "ncu --set full --clock-control none -k regex:'conv_silu|add_rmsnorm' python bench.py --steps 1 --warmup 1 --cpu-sample 0 --no-clocks   (PlantCaduceus_l32, B=256)")
+
+
+    dump(f"ssd_{TAG}.ncu-rep", f"{TAG}_ssd_ncu_summary.txt",
+         "ncu --set full --clock-control none --import-source on -k regex:'ssd_chunk_tc_kernel|gated_norm_sum' -s 4 -c 2 "
+         "python bench.py --workload long --model cad2-small --batch 8 --steps 1 --warmup 1 --cpu-sample 0 --no-clocks\n"
+         "PlantCAD2-Small (Mamba-2: d 768, 24 heads of 64, d_state 64), B = 8 x 8192 bp: S = 16 sequences, T = 131072 strand-tokens;\n"
+         "ssd_chunk_tc_kernel: grid (12 head pairs, 16 sequences, 2 directions), 64 chunks of 128 positions per CTA, one launch per layer.\n"
+         "algorithmic bytes per launch: 2 directions x T x (x 3 KB + B,C 256 B read, y 3 KB written) = 1.68 GB", stalls=True)
 
 
 if __name__ == "__main__":
