@@ -65,6 +65,7 @@ struct Workspace {
   uint8_t* ascii = nullptr;    // [B, L] staging for the host entry
   float* logits4 = nullptr;    // [B, 4] staging for the host entry
   int* pos = nullptr;          // [B] staging for the host entry
+  int* pos0 = nullptr;         // [B] zeros: positions for the head over the compact (pruned) last layer
 };
 
 }  // namespace
@@ -101,6 +102,8 @@ struct pcad_handle {
   // one executable graph per (B, L, token_idx), captured on the second call with that shape, replayed afterwards.
   struct ScoreGraph { int B, L, token_idx; bool seen_only; cudaGraphExec_t exec; int64_t launches; };
   std::vector<ScoreGraph> graphs;
+  bool prune_last = true;               // score-only calls: last layer computed only at the rows the head reads
+  bool last_pruned = false;             // set by run_backbone: ws.normed holds the compact [2B, d] rows
   bool time_parallel = true;            // Mamba-1: segmented scan when the sequential kernel's grid leaves the SMs empty
   bool use_graphs = true;
   cudaStream_t gstream = nullptr;       // capture / replay stream (the caller's may be the legacy default stream, which cannot capture)
@@ -321,7 +324,7 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
               const float* bias_r, void* y, int S, int L, int E, bool f32, cudaStream_t st,
               const void* wdt_f = nullptr, const void* wdt_r = nullptr, int segments = 1, float* seg_state = nullptr,
-              float* seg_sumd = nullptr) {
+              float* seg_sumd = nullptr, int Lrun = 0) {
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
     return fail(h, PCAD_ERR_INVALID, "biscan: E, ldbc, bc_off, ldz must be multiples of %d elements", vec);
@@ -346,9 +349,9 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
       return fail(h, PCAD_ERR_INVALID, "biscan: the in-kernel dt_proj needs bf16, both weights and ldbc >= 64");
     e = launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16), st, static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r));
   } else if (f32) {
-    e = launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float), st);
+    e = launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float), st, nullptr, nullptr, nullptr, Lrun);
   } else {
-    e = launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16), st);
+    e = launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16), st, nullptr, nullptr, nullptr, Lrun);
   }
 #undef PCAD_SCAN_ARGS
   CUDA_TRY(h, e);
@@ -382,6 +385,7 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
   const size_t o_ascii = take(static_cast<size_t>(B) * L);
   const size_t o_l4 = take(static_cast<size_t>(B) * 4 * sizeof(float));
   const size_t o_pos = take(static_cast<size_t>(B) * sizeof(int));
+  const size_t o_pos0 = take(static_cast<size_t>(B) * sizeof(int));
   if (ws && ws->base) {
     uint8_t* p = ws->base;
     ws->ids = p + o_ids; ws->hid = p + o_hid; ws->resid = p + o_res; ws->normed = p + o_nrm; ws->xz = p + o_xz;
@@ -390,6 +394,7 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
     ws->sumsq[0] = reinterpret_cast<float*>(p + o_ss0); ws->sumsq[1] = reinterpret_cast<float*>(p + o_ss1);
     ws->seg_state = reinterpret_cast<float*>(p + o_segs); ws->seg_sumd = reinterpret_cast<float*>(p + o_segd);
     ws->ascii = p + o_ascii; ws->logits4 = reinterpret_cast<float*>(p + o_l4); ws->pos = reinterpret_cast<int*>(p + o_pos);
+    ws->pos0 = reinterpret_cast<int*>(p + o_pos0);
   }
   return off;
 }
@@ -499,9 +504,23 @@ int run_mixer_m2(pcad_handle* h, LayerWeights& lw, int S, int L, cudaStream_t st
   return PCAD_OK;
 }
 
+// Score-only last layer: rows (s, row_s) of a [S*L, width] tensor -> compact [S, width]; row_s = idx for the forward strands
+// (s < B) and L-1-idx for the RC strands.  16-byte vectors.
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int S, int B, int L, int idx, int vec_per_row) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long long>(S) * vec_per_row) return;
+  const int s = static_cast<int>(gid / vec_per_row), v = static_cast<int>(gid % vec_per_row);
+  const int row = s < B ? idx : L - 1 - idx;
+  dst[gid] = src[(static_cast<long long>(s) * L + row) * vec_per_row + v];
+}
+
 // ---- the forward pass over the strand-major layout --------------------------------------------------
 // ids (u8 [B, L]) are already in ws.ids.  Leaves the final normed hidden state in ws.normed.
-int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
+// prune_idx >= 0 (score-only calls with one scored position per window): the LAST layer is computed only as far as the head
+// needs it -- the scan stops once both directions have reached the scored position (about half the steps at the window centre),
+// out_proj / residual / final norm run on the 2B rows the head reads, and ws.normed comes back COMPACT as [2B, d] (the head is then
+// called with L = 1, position 0).  Bit-identical to the full computation at those rows.
+int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st, int prune_idx = -1) {
   Workspace& ws = h->ws;
   const long long T = 2LL * B * L;
   const int S = 2 * B;
@@ -513,6 +532,7 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
   // squares in ws.sumsq[cur]; out_proj's epilogue adds into it, in_proj's epilogue applies rstd.  Otherwise the
   // block is norm kernel -> in_proj ... out_proj -> ws.hid, exactly the reference's order of roundings.
   int cur = 0;
+  h->last_pruned = false;
   const int parts = gemm_sumsq_parts(d);
   const int n_in = h->m2 ? h->DIP : 2 * E;          // in_proj output width and row pitch
   const long long ld_in = h->m2 ? h->DIPP : 2 * E;
@@ -528,6 +548,7 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
   for (int li = 0; li < h->cfg.n_layer; ++li) {
     LayerWeights& lw = h->layers[li];
     int rc;
+    bool pruned = false;
     if (!fused) {
       StageTimer tm(h, st, PCAD_ST_NORM);
       rc = op_add_rmsnorm(h, ws.hid, li == 0 ? nullptr : ws.resid, lw.norm_w, ws.normed, ws.resid, T, d, h->cfg.norm_eps, f32, res_f32, st);
@@ -587,14 +608,52 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st) {
                  static_cast<size_t>(S) * P * 2 * 2 * E * kScanN * sizeof(float) <= kSegStateBytes)
             P *= 2;
         }
+        pruned = prune_idx >= 0 && li == h->cfg.n_layer - 1 && P == 1 && h->prune_last && L >= 8;
+        const int Lrun = pruned ? (prune_idx > L - 1 - prune_idx ? prune_idx : L - 1 - prune_idx) + 1 : 0;
         rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
                        lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st,
-                       nullptr, nullptr, P, ws.seg_state, ws.seg_sumd);
+                       nullptr, nullptr, P, ws.seg_state, ws.seg_sumd, Lrun);
         if (P > 1) h->launch_count += 2;
       }
       if (rc) return rc;
     }
     }   // Mamba-1 mixer
+    if (pruned) {
+      h->last_pruned = true;
+      // compact tail: y and the residual stream at the 2B rows the head reads -> out_proj (+ residual) -> final norm, [2B, d]
+      const size_t a = h->act_size, rs = res_f32 ? 4 : a;
+      uint8_t* yc = static_cast<uint8_t*>(ws.delta[0]);                                  // [S, E]   (delta is dead after the scan)
+      uint8_t* rc_in = static_cast<uint8_t*>(ws.delta[1]);                               // [S, d]   residual rows
+      uint8_t* rc_out = rc_in + align_up(static_cast<size_t>(S) * d * 4, 1024);          // [S, d]   new residual / out_proj output
+      {
+        StageTimer tm(h, st, PCAD_ST_MISC, 2);
+        const int vy = static_cast<int>(E * a / 16), vr = static_cast<int>(d * rs / 16);
+        gather_rows_kernel<<<static_cast<unsigned>((static_cast<long long>(S) * vy + 255) / 256), 256, 0, st>>>(
+            static_cast<const uint4*>(ws.y), reinterpret_cast<uint4*>(yc), S, B, L, prune_idx, vy);
+        if (fused || li > 0)
+          gather_rows_kernel<<<static_cast<unsigned>((static_cast<long long>(S) * vr + 255) / 256), 256, 0, st>>>(
+              static_cast<const uint4*>(ws.resid), reinterpret_cast<uint4*>(rc_in), S, B, L, prune_idx, vr);
+        CUDA_TRY(h, cudaGetLastError());
+      }
+      {
+        StageTimer tm(h, st, PCAD_ST_OUT_PROJ);
+        if (fused) {
+          EpiParams ep;
+          ep.resid = reinterpret_cast<const bf16*>(rc_in);
+          ep.ld_res = d;
+          ep.sumsq_out = ws.sumsq[cur ^ 1];
+          ep.sumsq_parts = parts;
+          rc = op_linear(h, yc, lw.out_proj, rc_out, S, d, E, E, E, d, false, h->num_sms, st, kEpiResidual, ep);
+        } else {
+          rc = op_linear(h, yc, lw.out_proj, rc_out, S, d, E, E, E, d, f32, h->num_sms, st);
+        }
+        if (rc) return rc;
+      }
+      StageTimer tm(h, st, PCAD_ST_NORM);
+      if (fused) rc = op_add_rmsnorm(h, rc_out, nullptr, h->norm_f, ws.normed, nullptr, S, d, h->cfg.norm_eps, false, false, st);
+      else rc = op_add_rmsnorm(h, rc_out, li == 0 ? nullptr : rc_in, h->norm_f, ws.normed, nullptr, S, d, h->cfg.norm_eps, f32, res_f32, st);
+      return rc;
+    }
     {
       StageTimer tm(h, st, PCAD_ST_OUT_PROJ);
       if (fused) {
@@ -720,6 +779,7 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   h->fuse_dt = false;
   if (const char* fd = getenv("PCAD_FUSED_DT"))
     h->fuse_dt = fd[0] == '1' && !m2 && !h->f32 && h->RP >= kScanDtK && h->R <= kScanDtK && (h->E % 8) == 0;
+  if (const char* pl = getenv("PCAD_NO_PRUNE")) h->prune_last = pl[0] != '1';
   if (const char* tp = getenv("PCAD_NO_TIME_PARALLEL")) h->time_parallel = tp[0] != '1';
   if (const char* ng = getenv("PCAD_NO_GRAPH")) h->use_graphs = ng[0] != '1';
   if (const char* gm = getenv("PCAD_GRAPH_MAX_TOKENS")) h->graph_max_tokens = atoll(gm);
@@ -1018,13 +1078,16 @@ int score_core(pcad_handle* h, int B, int L, int token_idx, cudaStream_t st) {
   Workspace& ws = h->ws;
   const long long n = static_cast<long long>(B) * L;
   {
-    StageTimer tm(h, st, PCAD_ST_MISC, 2);
+    StageTimer tm(h, st, PCAD_ST_MISC, 3);
     tokenize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ascii, ws.ids, n, h->lut_dev, L, token_idx, h->mask_id);
     fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos, B, token_idx);
+    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos0, B, 0);
     CUDA_TRY(h, cudaGetLastError());
   }
-  int rc = run_backbone(h, B, L, st);
+  const bool prune = h->prune_last && !h->m2 && !h->fuse_dt && h->cfg.n_layer > 0;
+  int rc = run_backbone(h, B, L, st, prune ? token_idx : -1);
   if (rc) return rc;
+  if (prune && h->last_pruned) return run_head(h, B, 1, ws.pos0, 1, ws.logits4, st);   // ws.normed is compact [2B, d]
   return run_head(h, B, L, ws.pos, 1, ws.logits4, st);
 }
 

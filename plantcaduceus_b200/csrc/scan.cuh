@@ -247,7 +247,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
               const T* __restrict__ wdt_f, const T* __restrict__ wdt_r,
               const T* __restrict__ z, long long ldz, const float* __restrict__ A_f, const float* __restrict__ D_f,
               const float* __restrict__ bias_f, const float* __restrict__ A_r, const float* __restrict__ D_r,
-              const float* __restrict__ bias_r, T* y, int L, int E, const float* __restrict__ h0) {
+              const float* __restrict__ bias_r, T* y, int L, int E, const float* __restrict__ h0, int Lrun) {
   static_assert(!FUSEDT || (sizeof(T) == 2 && !PRECISE), "the in-kernel dt_proj is a bf16-path feature");
   extern __shared__ __align__(128) uint8_t scan_smem_raw[];
   // TMA destinations must be 128-byte aligned (1024 for the swizzled dt tiles); the runtime only promises 16 for the
@@ -269,7 +269,9 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   const bool active = e < E;
   const int seq = blockIdx.y;
   const long long row0 = static_cast<long long>(seq) * L;
-  const int nch = (L + kScanTC - 1) / kScanTC;
+  // Lrun <= L: number of steps each direction takes.  Lrun < L is the score-only LAST layer, where y is wanted at one position p
+  // only: after max(p, L-1-p) + 1 steps both directions have been there (rows further on hold parked partials nobody reads).
+  const int nch = (Lrun + kScanTC - 1) / kScanTC;
   constexpr int VEC = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int SEGS = kScanCH / VEC;              // 16-byte segments per 128-channel row
   constexpr uint32_t kStageBytes = sizeof(Stage);
@@ -320,7 +322,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     if (tid == 0 && c + 1 < nch) issue(c + 1, stage ^ 1);
     const Stage& s = sm.st[stage];
     const int i0 = c * kScanTC;
-    const int nsteps = min(kScanTC, L - i0);
+    const int nsteps = min(kScanTC, Lrun - i0);
     const bool has_final = (L - 1 - (i0 + nsteps - 1)) < i0 + nsteps;
     mbar_wait(&full_bar[stage], (c >> 1) & 1);
     if constexpr (FUSEDT) {
@@ -564,7 +566,7 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
                                  const float* D_r, const float* bias_r, T* y, int S, int L, int E,
                                  cudaStream_t stream, const T* wdt_f = nullptr, const T* wdt_r = nullptr,
-                                 const float* h0 = nullptr) {
+                                 const float* h0 = nullptr, int Lrun = 0) {
   size_t smem = sizeof(ScanShared<T, FUSEDT>) + (FUSEDT ? 1024 : 128);   // + alignment slack for the TMA destinations
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static unsigned long long attr_done = 0;
@@ -586,7 +588,8 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
   if (!ok) return cudaErrorInvalidValue;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
   biscan_kernel<T, PRECISE, FUSEDT><<<grid, kScanThreads, smem, stream>>>(
-      tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], wdt_f, wdt_r, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E, h0);
+      tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], wdt_f, wdt_r, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E, h0,
+      (Lrun > 0 && Lrun < L) ? Lrun : L);
   return cudaGetLastError();
 }
 

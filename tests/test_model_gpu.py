@@ -321,3 +321,31 @@ def test_small_batch_cuda_graph_replay_is_bit_identical(Model, cuda_device, monk
     eager.set_tokenizer(tok)
     for _ in range(3):
         assert torch.equal(graphed.score_windows_host(batches[1], 255), eager.score_windows_host(batches[1], 255))
+
+
+@pytest.mark.parametrize("kw,dtype", [(dict(d_model=256, n_layer=3), torch.bfloat16), (dict(d_model=128, n_layer=1), torch.bfloat16),
+                                      (dict(d_model=256, n_layer=2, residual_in_fp32=True), torch.bfloat16),
+                                      (dict(d_model=128, n_layer=2), torch.float32)])
+def test_score_only_last_layer_pruning_is_bit_identical(Model, cuda_device, monkeypatch, kw, dtype):
+    """Score-only calls compute the last layer only as far as the head needs it (the scan stops once both directions have reached
+    the scored position; out_proj, residual add and final norm run on the 2B rows the head reads).  Same bits as the full
+    computation (PCAD_NO_PRUNE=1) and as the logits of the full forward, for positions at the centre, the edges and off-centre,
+    even and odd window lengths."""
+    cfg = CaduceusConfig(**kw)
+    sd = random_init_state_dict(cfg, seed=17)
+    rng = np.random.default_rng(6)
+    pruned = Model.from_pretrained(sd, config=cfg, torch_dtype=dtype).to(cuda_device)
+    monkeypatch.setenv("PCAD_NO_PRUNE", "1")
+    full = Model.from_pretrained(sd, config=cfg, torch_dtype=dtype).to(cuda_device)
+    tok = CharDNATokenizer()
+    for L, idxs in ((512, (255, 0, 511, 100, 300)), (301, (150, 7, 299)), (33, (16, 32))):
+        a = torch.from_numpy(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=(5, L))).pin_memory()
+        for idx in idxs:
+            got = pruned.score_windows_host(a, idx).clone()
+            want = full.score_windows_host(a, idx).clone()
+            assert torch.equal(got, want), (L, idx)
+            ids = torch.from_numpy(tok.encode_bytes(a.numpy()).astype(np.int64))
+            ids[:, idx] = tok.mask_token_id
+            logits = full(input_ids=ids.to(cuda_device)).logits[:, idx, 3:7].cpu()
+            assert torch.equal(got, logits), (L, idx)
+    assert pruned.launch_count() != full.launch_count()
