@@ -10,7 +10,7 @@ synthetic 512-bp windows per GPU (PlantCaduceus_l32, bf16, 256 windows, position
 published architecture): tokenise -> mask -> 32-layer RC BiMamba forward -> LM head at the masked position -> 4 logits
 (a,c,g,t) per variant.
 
-  value : variants/s, inputs (token ids) already resident in HBM   (pcad_score_masked)
+  value : variants/s, inputs (token ids) already resident in HBM   (pcad_score_masked_at)
   e2e   : variants/s through the reference-facing host call: pinned ASCII windows on the host -> H2D ->
           device tokenise+mask -> forward -> D2H of [B,4] fp32 logits -> sync   (pcad_score_windows_host)
   roofline     : dominant kernel, algorithmic bytes (or FLOPs) / live CUDA-event time
@@ -344,15 +344,18 @@ def run_ours(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        timed.per_rank_ms = [ms]
         if world > 1:
             t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            timed.per_rank_ms = [float(x.item()) for x in allt]
+            ms = max(timed.per_rank_ms)
         return ms
 
     if wl == "snp":
-        def step_device(i):
-            results[i] = model.score_masked(dev_ids[i % n_batches], dev_pos[i % n_batches], check_ids=False)[:, 0]
+        def step_device(i):   # token ids resident in HBM, one scored index (tokenIdx) for every window
+            results[i] = model.score_masked(dev_ids[i % n_batches], TOKEN_IDX, check_ids=False)[:, 0]
 
         def step_host(i):
             model.score_windows_host(host_ascii[i % n_batches], TOKEN_IDX, out=host_out)
@@ -400,13 +403,20 @@ def run_ours(args):
 
     for i in range(W):
         step_device(i)
-    sampler = ClockSampler(local)
-    if rank == 0 and not args.no_clocks:
+    sampler = ClockSampler(local)          # every rank samples its own GPU: the slowest rank sets the multi-GPU number
+    if not args.no_clocks:
         sampler.start()
     launches0 = model.launch_count()
     ms_total = timed(step_device, K, gather=wl != "long")
+    per_rank_ms = list(timed.per_rank_ms)
     launches = model.launch_count() - launches0
-    clocks = sampler.stop() if (rank == 0 and not args.no_clocks) else None
+    clocks = sampler.stop() if not args.no_clocks else None
+    per_rank_mhz = None
+    if world > 1 and clocks is not None:
+        t = torch.tensor([float(clocks.get("sm_mhz") or 0.0)], device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_mhz = [float(x.item()) for x in allt]
     per_item = 3 if wl == "mutagenesis" else 1       # variants per masked forward
     value = world * B * K * per_item / (ms_total * 1e-3)
 
@@ -508,6 +518,10 @@ def run_ours(args):
     line["stage_share"] = {k: round(v / total_stage_ms, 4) for k, v in stage_ms.items()} if total_stage_ms > 0 else None
     if clocks is not None:
         line["clocks"] = clocks
+    if world > 1:
+        # the timed value is the MAX over ranks: with no data-path collective, what separates N GPUs from N x one GPU is the
+        # slowest GPU's power-capped clock, visible here rank by rank
+        line["ranks"] = {"ms_per_step": [round(m / K, 2) for m in per_rank_ms], "sm_mhz": per_rank_mhz}
     if world == 1 and args.cpu_sample > 0:
         n = 1 if wl == "long" else args.cpu_sample
         if wl == "snp":

@@ -100,6 +100,12 @@ int pcad_forward(pcad_handle* h, const int64_t* ids_dev, int B, int L,
 int pcad_score_masked(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos_dev,
                       int B, int L, int n_mask, float* logits4_dev, void* stream);
 
+/* pcad_score_masked for the reference's own case -- ONE scored position, the same index in every window
+ * (extract_logits: logits[:, tokenIdx, [a,c,g,t]], zero_shot_score.py:117-118).  Knowing the position on the host lets the engine
+ * compute the last layer only as far as the head needs it.  Output float32 [B, 4], bit-identical to pcad_score_masked. */
+int pcad_score_masked_at(pcad_handle* h, const uint8_t* ids_dev, int token_idx, int B, int L,
+                         float* logits4_dev, void* stream);
+
 /* Replaces: model(input_ids, output_hidden_states=True).hidden_states[-1][:, tokenIdx, :]  (extract_embeddings,
  * train_XGBoost.py:104-105) without materialising [B, L, 2*d_model]: ids_dev uint8 [B, L] (masked or not, as the caller
  * wants), pos_dev int32 [B, n_pos]; hidden_dev receives [B, n_pos, 2*d_model] in the model dtype (forward half, then the

@@ -20,7 +20,7 @@ ABI_VERSION = 2
 
 EXPORTS = (
     "pcad_abi_version", "pcad_create", "pcad_destroy", "pcad_last_error", "pcad_set_weight", "pcad_finalize",
-    "pcad_set_tokenizer", "pcad_take_id_error", "pcad_hidden_at", "pcad_forward", "pcad_score_masked", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
+    "pcad_set_tokenizer", "pcad_take_id_error", "pcad_hidden_at", "pcad_forward", "pcad_score_masked", "pcad_score_masked_at", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
     "pcad_workspace_bytes", "pcad_set_profiling", "pcad_get_profile", "pcad_launch_count",
     "pcad_op_linear", "pcad_op_linear_residual", "pcad_op_linear_rowscale", "pcad_op_sumsq_parts",
     "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_biscan", "pcad_op_biscan_segmented", "pcad_op_biscan_dt", "pcad_op_prep_dt_weight",
@@ -69,6 +69,7 @@ def load() -> C.CDLL:
     lib.pcad_hidden_at.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
     lib.pcad_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     lib.pcad_score_masked.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.pcad_score_masked_at.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.pcad_score_windows_host.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.pcad_score_windows_dev.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.pcad_extract_windows.argtypes = [vp, vp, i64, vp, i32, i32, i32, vp, vp]

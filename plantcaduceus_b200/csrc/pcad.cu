@@ -1214,6 +1214,33 @@ int pcad_score_masked(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos
   return run_head(h, B, L, pos_dev, n_mask, logits4_dev, st);
 }
 
+int pcad_score_masked_at(pcad_handle* h, const uint8_t* ids_dev, int token_idx, int B, int L, float* logits4_dev, void* stream) {
+  int rc = check_call(h, B, L);
+  if (rc) return rc;
+  if (B == 0 || L == 0) return PCAD_OK;
+  if (!ids_dev || !logits4_dev) return fail(h, PCAD_ERR_INVALID, "null argument");
+  if (token_idx < 0 || token_idx >= L) return fail(h, PCAD_ERR_INVALID, "token_idx %d outside [0, %d)", token_idx, L);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = ensure_workspace(h, B, L);
+  if (rc) return rc;
+  Workspace& ws = h->ws;
+  {
+    StageTimer tm(h, st, PCAD_ST_MISC, 3);
+    const long long n = static_cast<long long>(B) * L;
+    ids_u8_check_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ids_dev, ws.ids, n, h->V, h->bad_flag);
+    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos, B, token_idx);
+    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos0, B, 0);
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  // one scored position, the same in every window: the last layer is computed only at the rows the head reads
+  const bool prune = h->prune_last && !h->m2 && !h->fuse_dt && h->cfg.n_layer > 0;
+  rc = run_backbone(h, B, L, st, prune ? token_idx : -1);
+  if (rc) return rc;
+  if (prune && h->last_pruned) return run_head(h, B, 1, ws.pos0, 1, logits4_dev, st);
+  return run_head(h, B, L, ws.pos, 1, logits4_dev, st);
+}
+
 int pcad_hidden_at(pcad_handle* h, const uint8_t* ids_dev, const int32_t* pos_dev, int B, int L, int n_pos, void* hidden_dev, void* stream) {
   int rc = check_call(h, B, L);
   if (rc) return rc;

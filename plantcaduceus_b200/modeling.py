@@ -235,13 +235,23 @@ class CaduceusForMaskedLM:
             raise IndexError(msg.decode() if msg else "token id out of range")
 
     def score_masked(self, ids_u8: torch.Tensor, positions: torch.Tensor, check_ids: bool = True) -> torch.Tensor:
-        """ids_u8: uint8 [B, L] token ids (already masked) on the device; positions: int32 [B, n_mask].
+        """ids_u8: uint8 [B, L] token ids (already masked) on the device; positions: int32 [B, n_mask], or a Python int when every
+        window is scored at the same index (the reference's tokenIdx; lets the engine prune the last layer).
         Returns float32 [B, n_mask, 4] logits in a,c,g,t order (extract_logits / _masked_probs gather).
         ``check_ids=False`` keeps the call asynchronous: an out-of-range id is then reported by the next checking call."""
         self._require_handle()
         ids = ids_u8.to(device=self.device, dtype=torch.uint8).contiguous()
-        pos = positions.to(device=self.device, dtype=torch.int32).contiguous()
         B, L = ids.shape
+        if isinstance(positions, int):
+            # the reference's own case: one scored index shared by every window (extract_logits, tokenIdx) -> [B, 1, 4]
+            with torch.cuda.device(self.device):
+                out = torch.empty((B, 1, 4), dtype=torch.float32, device=self.device)
+                if B > 0 and L > 0:
+                    _lib.check(self._lib.pcad_score_masked_at(self._handle, C.c_void_p(ids.data_ptr()), int(positions), B, L,
+                                                              C.c_void_p(out.data_ptr()), self._stream()), self._handle)
+                    self._raise_on_bad_ids(check_ids)
+            return out
+        pos = positions.to(device=self.device, dtype=torch.int32).contiguous()
         if pos.dim() == 1:
             pos = pos[:, None]
         n_mask = pos.shape[1]

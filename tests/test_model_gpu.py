@@ -348,4 +348,7 @@ def test_score_only_last_layer_pruning_is_bit_identical(Model, cuda_device, monk
             ids[:, idx] = tok.mask_token_id
             logits = full(input_ids=ids.to(cuda_device)).logits[:, idx, 3:7].cpu()
             assert torch.equal(got, logits), (L, idx)
+            # ids resident on the device + one shared index (pcad_score_masked_at) and per-row positions (pcad_score_masked)
+            assert torch.equal(pruned.score_masked(ids.to(torch.uint8), idx).cpu()[:, 0], got)
+            assert torch.equal(pruned.score_masked(ids.to(torch.uint8), torch.full((5, 1), idx, dtype=torch.int32)).cpu()[:, 0], got)
     assert pruned.launch_count() != full.launch_count()

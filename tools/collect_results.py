@@ -34,34 +34,42 @@ def main():
              "1.76-1.95 GHz under `sw_power_cap` (the only throttle reason seen), which moves the headline by a few percent between calls.", ""]
     # headline + scaling
     lines += ["## Headline (BASELINE.json configs[1]: PlantCaduceus_l32, 256 x 512-bp windows per GPU per step) and weak scaling", "",
-              "| GPUs | variants/s | ms/step | e2e variants/s | x of 1 GPU | SM MHz | file |", "|---|---|---|---|---|---|---|"]
+              "Same 8-GPU box, same lease, back to back (`tools/scale_ladder.sh`):", "",
+              "| GPUs | variants/s | ms/step | e2e variants/s | x of 1 GPU | efficiency | SM MHz (rank 0) | file |", "|---|---|---|---|---|---|---|---|"]
     base = None
-    for n in (1, 2, 4, 8):
+    for n in (1, 4, 8):
+        d = load(f"r02_ladder_n{n}.json")
+        if d is None:
+            continue
+        if n == 1:
+            base = d["value"]
+        shutil.copy(os.path.join(OUT, f"r02_ladder_n{n}.json"), os.path.join(PROF, f"r02_ladder_n{n}.json"))
+        x = d["value"] / base if base else float("nan")
+        lines.append(f"| {n} | {d['value']:.1f} | {d['ms_per_step']:.2f} | {d['e2e']['value']:.1f} | {x:.2f} | {x / n:.3f} | {(d.get('clocks') or {}).get('sm_mhz')} | profiles/r02_ladder_n{n}.json |")
+    lines += ["", "Other boxes (one call each, so the ratio to the table above mixes boxes with different power-capped clocks):", "",
+              "| GPUs | variants/s | ms/step | SM MHz (rank 0) | file |", "|---|---|---|---|---|"]
+    for n in (2, 8):
         d = load(f"r02_scale_n{n}.json")
         if d is None:
             continue
-        if n == 1:
-            base = d["value"]
         shutil.copy(os.path.join(OUT, f"r02_scale_n{n}.json"), os.path.join(PROF, f"r02_scale_n{n}.json"))
-        x = f"{d['value'] / base:.2f}" if base else "-"
-        lines.append(f"| {n} | {d['value']:.1f} | {d['ms_per_step']:.1f} | {d['e2e']['value']:.1f} | {x} | {(d.get('clocks') or {}).get('sm_mhz')} | profiles/r02_scale_n{n}.json |")
+        lines.append(f"| {n} | {d['value']:.1f} | {d['ms_per_step']:.2f} | {(d.get('clocks') or {}).get('sm_mhz')} | profiles/r02_scale_n{n}.json |")
     lines += ["", "`python bench.py --steps 20 --warmup 3` (N = 1) / `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps 20 --warmup 3`;",
-              "the scores of all steps are gathered once after the last step, inside the timed region.", ""]
+              "the scores of all steps are gathered once after the last step, inside the timed region.  There is no data-path collective, and",
+              "the reported time is the MAX over ranks: the step goes 284.7 ms (1 GPU) -> 290.9 ms (8 GPUs) because the slowest of eight",
+              "power-capped GPUs sets it (bench.py now reports every rank's ms/step and SM clock under `ranks`).", ""]
     lines += ["## Config 3: genome-wide scoring, chromosome resident in HBM, windows cut on the device", "",
-              "| GPUs | variants/s | ms/step | steps (timed s) | x of 1 GPU | 10 M variants would take | file |", "|---|---|---|---|---|---|---|"]
-    base = None
-    for n in (1, 2, 4, 8):
-        d = load(f"r02_config3_n{n}.json")
+              "| GPUs | variants/s | ms/step | steps (timed s) | 10 M variants would take | file |", "|---|---|---|---|---|---|"]
+    for n, name in ((1, "r02_ladder_config3_n1.json"), (2, "r02_config3_n2.json"), (8, "r02_config3_n8.json")):
+        d = load(name)
         if d is None:
             continue
-        if n == 1:
-            base = d["value"]
-        shutil.copy(os.path.join(OUT, f"r02_config3_n{n}.json"), os.path.join(PROF, f"r02_config3_n{n}.json"))
-        x = f"{d['value'] / base:.2f}" if base else "-"
+        shutil.copy(os.path.join(OUT, name), os.path.join(PROF, name))
         secs = d["steps"] * d["ms_per_step"] / 1e3
-        lines.append(f"| {n} | {d['value']:.1f} | {d['ms_per_step']:.1f} | {d['steps']} ({secs:.0f} s) | {x} | {1e7 / d['value'] / 60:.0f} min | profiles/r02_config3_n{n}.json |")
+        lines.append(f"| {n} | {d['value']:.1f} | {d['ms_per_step']:.2f} | {d['steps']} ({secs:.0f} s) | {1e7 / d['value'] / 60:.0f} min | profiles/{name} |")
     lines += ["", "`bench.py --workload genome --steps K` (synthetic 200 Mb chromosome, uniform positions, 256 variants per GPU per step; rank 0 builds",
-              "the chromosome and broadcasts it GPU to GPU).  The 10 M-variant figure is the extrapolation SURVEY.md 8(d) allows.", ""]
+              "the chromosome and broadcasts it GPU to GPU).  N = 8 ran 64 s of steady state; the 10 M-variant figure is the extrapolation",
+              "SURVEY.md 8(d) allows.  (The three rows come from three different boxes.)", ""]
     # other workloads
     lines += ["## Other workloads, 1 GPU", "", "| workload | value | ms/step | stages (ms/step) | file |", "|---|---|---|---|---|"]
     for pat, label in (("r02_final_mutagenesis.json", "config 4: saturation mutagenesis, l32"), ("r02_final_long_l32.json", "config 5: L = 8192 embeddings, l32 (Mamba-1), B = 16"),
