@@ -76,7 +76,7 @@ struct pcad_handle {
   int num_sms = 148;
   int d = 0, E = 0, N = 16, R = 0, RP = 0, V = 8;
   bool m2 = false;                     // Mamba-2 / SSD mixer (PlantCAD2)
-  bool ssd_seq = false;                // Mamba-2 bf16: run the sequential-recurrence kernel instead of the tcgen05 SSD (A/B switch)
+  int ssd_impl = 0;                    // Mamba-2 bf16 A/B switch: 0 chunked SSD on tcgen05, 1 sequential recurrence
   int H = 0, CD = 0, DIP = 0, DIPP = 0;   // Mamba-2: heads, conv channels (x|B|C), in_proj width (z|x|B|C|dt) and its padded pitch
   bool f32 = false;
   bool fuse_dt = false;                // bf16: dt_proj computed inside the scan (mma.sync), no dt_proj launches, no delta in HBM
@@ -425,7 +425,9 @@ int ensure_workspace(pcad_handle* h, int B, int L) {
 // ---- Mamba-2 mixer between in_proj and out_proj: conv + SiLU over x|B|C, SSD scan per direction, gated norms + add ------
 int op_ssd_scan(pcad_handle* h, const void* xbc_f, const void* xbc_r, long long ld_xbc, const void* dt_raw, long long ld_dt,
                 const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r, const float* bias_r,
-                void* y_f, void* y_r, int S, int L, int H, bool f32, bool sequential, cudaStream_t st) {
+                void* y_f, void* y_r, int S, int L, int H, bool f32, int impl, cudaStream_t st) {
+  // impl (bf16): 0 = chunked SSD on tcgen05 (ssd_chunk_tc_kernel), 1 = sequential recurrence
+  const bool sequential = impl == 1;
   if (S <= 0 || L <= 0) return PCAD_OK;
   if (H <= 0 || S > 65535) return fail(h, PCAD_ERR_INVALID, "ssd_scan: need H > 0 and at most 65535 sequences per call");
   cudaError_t e;
@@ -493,7 +495,7 @@ int run_mixer_m2(pcad_handle* h, LayerWeights& lw, int S, int L, cudaStream_t st
   {
     StageTimer tm(h, st, PCAD_ST_SCAN);
     rc = op_ssd_scan(h, ws.xc[0], ws.xc[1], CD, zx + static_cast<size_t>(E + CD) * a, h->DIPP, lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias,
-                     lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.delta[0], ws.delta[1], S, L, H, f32, h->ssd_seq, st);
+                     lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.delta[0], ws.delta[1], S, L, H, f32, h->ssd_impl, st);
     if (rc) return rc;
   }
   {
@@ -768,7 +770,7 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
     h->DIPP = (h->DIP + 7) / 8 * 8;
     h->R = 0;
     h->RP = 0;
-    if (const char* sq = getenv("PCAD_SSD_SEQ")) h->ssd_seq = sq[0] == '1';
+    if (const char* sq = getenv("PCAD_SSD_SEQ")) h->ssd_impl = sq[0] == '1' ? 1 : 0;
   }
   h->V = cfg->vocab_size;
   h->f32 = cfg->dtype == PCAD_F32;
@@ -1423,7 +1425,7 @@ int pcad_op_ssd_scan(const void* xbc_f, const void* xbc_r, int64_t ld_xbc, const
                      void* y_r, int S, int L, int H, int dtype, int sequential, void* stream) {
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_ssd_scan(op_scratch(), xbc_f, xbc_r, ld_xbc, dt_raw, ld_dt, A_f, D_f, dt_bias_f, A_r, D_r, dt_bias_r, y_f,
-                                       y_r, S, L, H, dtype == PCAD_F32, sequential != 0, static_cast<cudaStream_t>(stream)));
+                                       y_r, S, L, H, dtype == PCAD_F32, sequential, static_cast<cudaStream_t>(stream)));
 }
 
 int pcad_op_gated_norm_sum(const void* y_f, const void* y_r, const void* z, int64_t ldz, const float* w_f, const float* w_r, void* out,

@@ -360,6 +360,17 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
       tma_load_3d(sm + SsdSmem::kX1, tm, tma_bar, (2 * hp + 1) * kSsdP, p0, seq);
       tma_load_3d(sm + SsdSmem::kB, tm, tma_bar, E, p0, seq);
       tma_load_3d(sm + SsdSmem::kC, tm, tma_bar, E + kSsdN, p0, seq);
+      // the tiles are single-buffered (shared memory is what caps the kernel at 2 CTAs/SM), so the next chunk's load cannot be
+      // issued early; pulling it into L2 now at least takes the HBM latency off the next iteration's critical path
+      if (it + 1 < nch) {
+        const int pn = (dir ? nch - 2 - it : it + 1) * kSsdQ;
+        tma_prefetch_l2_3d(tm, (2 * hp) * kSsdP, pn, seq);
+        tma_prefetch_l2_3d(tm, (2 * hp + 1) * kSsdP, pn, seq);
+        if (hp == 0) {   // B and C are shared by the head pairs of this (sequence, direction): one CTA prefetches them
+          tma_prefetch_l2_3d(tm, E, pn, seq);
+          tma_prefetch_l2_3d(tm, E + kSsdN, pn, seq);
+        }
+      }
     }
     // ---- dt, log-decay and its cumulative sum in scan order
     {

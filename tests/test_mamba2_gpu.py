@@ -113,15 +113,16 @@ def test_ssd_scan_tcgen05_matches_oracle(lib, cuda_device, S, L, H):
     scale; it must also be at least as close to the oracle as the sequential bf16 kernel up to that rounding."""
     xbc, dt_raw, ld_dt, A, D, bias = ssd_inputs(S, L, H, 11 + L + H, torch.bfloat16)
     want = oracle_ssd(xbc, dt_raw, A, D, bias, S, L, H) if L <= 1024 else None
-    seq = run_ssd(lib, cuda_device, xbc, dt_raw, ld_dt, A, D, bias, S, L, H, BF16, True)
-    got = run_ssd(lib, cuda_device, xbc, dt_raw, ld_dt, A, D, bias, S, L, H, BF16, False)
+    seq = run_ssd(lib, cuda_device, xbc, dt_raw, ld_dt, A, D, bias, S, L, H, BF16, 1)
     ref = want if want is not None else seq
-    for k in range(2):
-        assert not torch.isnan(got[k]).any(), report(got, ref, S, L, H, "tc")
-        scale = ref[k].abs().max().item()
-        err = (got[k] - ref[k]).abs().max().item()
-        assert err <= 2 ** -5 * scale, f"max err {err:.4g} scale {scale:.4g}\n" + report(got, ref, S, L, H, "tc")
-        assert (got[k] - ref[k]).abs().mean().item() <= 2 ** -8 * scale
+    for impl, label in ((0, "tcgen05"),):
+        got = run_ssd(lib, cuda_device, xbc, dt_raw, ld_dt, A, D, bias, S, L, H, BF16, impl)
+        for k in range(2):
+            assert not torch.isnan(got[k]).any(), label + "\n" + report(got, ref, S, L, H, "tc")
+            scale = ref[k].abs().max().item()
+            err = (got[k] - ref[k]).abs().max().item()
+            assert err <= 2 ** -5 * scale, f"{label}: max err {err:.4g} scale {scale:.4g}\n" + report(got, ref, S, L, H, "tc")
+            assert (got[k] - ref[k]).abs().mean().item() <= 2 ** -8 * scale, label
 
 
 @pytest.mark.parametrize("rows,E", [(77, 256), (64, 1536), (5, 3072)])
