@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PCAD_ABI_VERSION 2
+#define PCAD_ABI_VERSION 3
 
 typedef enum {
   PCAD_OK = 0,
@@ -221,13 +221,12 @@ int pcad_op_biscan_segmented(const void* u_f, const void* delta_f, const void* b
                              void* y, int S, int L, int E, int segments, float* seg_state, float* seg_sumd,
                              int dtype, void* stream);
 
-/* The same with Mamba.dt_proj [F.linear(dt, dt_proj.weight)] computed inside the scan kernel (bf16 only): dbc_* are the
- * x_proj outputs [S*L, ldbc] (dt in columns [0, R), B at [bc_off, bc_off+16), C at [bc_off+16, bc_off+32); ldbc >= 64),
- * wdt_* the dt_proj weights re-laid by pcad_op_prep_dt_weight ([E, R] with row pitch ldw -> [E, 64], R <= 64).  Delta is
- * rounded to bf16 where the GEMM would have rounded it, so the result matches pcad_op_linear + pcad_op_biscan. */
-int pcad_op_prep_dt_weight(const void* W, int64_t ldw, void* out, int E, int R, void* stream);
+/* The same with Mamba.dt_proj [F.linear(dt, dt_proj.weight)] computed inside the scan kernel on the tensor core (bf16 only):
+ * dbc_* are the x_proj outputs [S*L, ldbc] (dt in columns [0, R), B at [bc_off, bc_off+16), C at [bc_off+16, bc_off+32);
+ * ldbc >= 64), wdt_* the dt_proj weights [E, R] with row pitch ldw (elements, a multiple of 8; R <= 64).  Delta is rounded
+ * to bf16 where the GEMM would have rounded it, so the result matches pcad_op_linear + pcad_op_biscan. */
 int pcad_op_biscan_dt(const void* u_f, const void* dbc_f, const void* u_r, const void* dbc_r, int64_t ldbc, int bc_off,
-                      const void* wdt_f, const void* wdt_r, const void* z, int64_t ldz,
+                      const void* wdt_f, const void* wdt_r, int64_t ldw, int R, const void* z, int64_t ldz,
                       const float* A_f, const float* D_f, const float* dt_bias_f,
                       const float* A_r, const float* D_r, const float* dt_bias_r,
                       void* y, int S, int L, int E, void* stream);

@@ -16,14 +16,14 @@ LIB_PATH = _HERE / "libpcad.so"
 PCAD_BF16, PCAD_F32, PCAD_F16 = 0, 1, 2
 STAGES = ("embed", "norm", "in_proj", "conv", "x_proj", "dt_proj", "scan", "out_proj", "head", "misc", "gnorm")
 PCAD_MIXER_MAMBA1, PCAD_MIXER_MAMBA2 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "pcad_abi_version", "pcad_create", "pcad_destroy", "pcad_last_error", "pcad_set_weight", "pcad_finalize",
     "pcad_set_tokenizer", "pcad_take_id_error", "pcad_hidden_at", "pcad_forward", "pcad_score_masked", "pcad_score_masked_at", "pcad_score_windows_host", "pcad_score_windows_dev", "pcad_extract_windows", "pcad_tokenize",
     "pcad_workspace_bytes", "pcad_set_profiling", "pcad_get_profile", "pcad_launch_count",
     "pcad_op_linear", "pcad_op_linear_residual", "pcad_op_linear_rowscale", "pcad_op_sumsq_parts",
-    "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_biscan", "pcad_op_biscan_segmented", "pcad_op_biscan_dt", "pcad_op_prep_dt_weight",
+    "pcad_op_add_rmsnorm", "pcad_op_conv_silu", "pcad_op_biscan", "pcad_op_biscan_segmented", "pcad_op_biscan_dt",
     "pcad_op_ssd_scan", "pcad_op_gated_norm_sum",
 )
 
@@ -85,8 +85,7 @@ def load() -> C.CDLL:
     lib.pcad_op_sumsq_parts.argtypes = [i32]
     lib.pcad_op_add_rmsnorm.argtypes = [vp, vp, vp, vp, vp, i64, i32, C.c_float, i32, i32, vp]
     lib.pcad_op_conv_silu.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
-    lib.pcad_op_prep_dt_weight.argtypes = [vp, i64, vp, i32, i32, vp]
-    lib.pcad_op_biscan_dt.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.pcad_op_biscan_dt.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.pcad_op_biscan.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp,
                                    i32, i32, i32, i32, vp]
     lib.pcad_op_biscan_segmented.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp,

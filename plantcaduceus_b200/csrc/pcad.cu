@@ -29,7 +29,6 @@ struct DirWeights {
   float* conv_b = nullptr;   // [E]
   void* x_proj = nullptr;    // [RP, E] act dtype, rows >= R+2N zero
   void* dt_proj = nullptr;   // [E, R] act dtype
-  void* dt_proj_p = nullptr; // [E, 64] bf16 in mma B-fragment order (prep_dt_weight_kernel): dt_proj fused into the scan
   float* dt_bias = nullptr;  // [E]
   float* A = nullptr;        // [E, N] = -exp(A_log)
   float* D = nullptr;        // [E]
@@ -79,7 +78,7 @@ struct pcad_handle {
   int ssd_impl = 0;                    // Mamba-2 bf16 A/B switch: 0 chunked SSD on tcgen05, 1 sequential recurrence
   int H = 0, CD = 0, DIP = 0, DIPP = 0;   // Mamba-2: heads, conv channels (x|B|C), in_proj width (z|x|B|C|dt) and its padded pitch
   bool f32 = false;
-  bool fuse_dt = false;                // bf16: dt_proj computed inside the scan (mma.sync), no dt_proj launches, no delta in HBM
+  bool fuse_dt = false;                // bf16: dt_proj computed inside the scan (tcgen05), no dt_proj launches, no delta in HBM
   bool fuse_norm = false;   // bf16 activations + bf16 residual: add+RMSNorm folded into the out_proj / in_proj epilogues
   size_t act_size = 2;
   bool finalized = false;
@@ -323,8 +322,8 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
               const void* delta_r, const void* bc_r, long long ldbc, int bc_off, const void* z, long long ldz,
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
               const float* bias_r, void* y, int S, int L, int E, bool f32, cudaStream_t st,
-              const void* wdt_f = nullptr, const void* wdt_r = nullptr, int segments = 1, float* seg_state = nullptr,
-              float* seg_sumd = nullptr, int Lrun = 0) {
+              const void* wdt_f = nullptr, const void* wdt_r = nullptr, long long ldw = 0, int R = 0, int segments = 1,
+              float* seg_state = nullptr, float* seg_sumd = nullptr, int Lrun = 0) {
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
     return fail(h, PCAD_ERR_INVALID, "biscan: E, ldbc, bc_off, ldz must be multiples of %d elements", vec);
@@ -344,14 +343,15 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
     CUDA_TRY(h, e);
     return PCAD_OK;
   }
-  if (fused_dt) {   // delta_* are the x_proj outputs, dt_proj runs inside the kernel
-    if (f32 || !wdt_f || !wdt_r || ldbc < kScanDtK)
-      return fail(h, PCAD_ERR_INVALID, "biscan: the in-kernel dt_proj needs bf16, both weights and ldbc >= 64");
-    e = launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16), st, static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r));
+  if (fused_dt) {   // delta_* are the x_proj outputs, dt_proj runs inside the kernel (tcgen05)
+    if (f32 || !wdt_f || !wdt_r || ldbc < kScanDtK || R <= 0 || R > kScanDtK || ldw < R || ldw % 8)
+      return fail(h, PCAD_ERR_INVALID, "biscan: the in-kernel dt_proj needs bf16, both weights (R <= 64, row pitch a multiple of 8) and ldbc >= 64");
+    e = launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16), st, static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r), ldw, R,
+                                         nullptr, Lrun);
   } else if (f32) {
-    e = launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float), st, nullptr, nullptr, nullptr, Lrun);
+    e = launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float), st, nullptr, nullptr, 0, 0, nullptr, Lrun);
   } else {
-    e = launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16), st, nullptr, nullptr, nullptr, Lrun);
+    e = launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16), st, nullptr, nullptr, 0, 0, nullptr, Lrun);
   }
 #undef PCAD_SCAN_ARGS
   CUDA_TRY(h, e);
@@ -579,13 +579,26 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st, int prune_idx = 
       rc = op_conv(h, ws.xz, 2 * E, lw.dir[0].conv_w, lw.dir[0].conv_b, lw.dir[1].conv_w, lw.dir[1].conv_b, ws.xc[0], ws.xc[1], S, L, E, f32, st);
       if (rc) return rc;
     }
+    // low batch / long context: cut every sequence into P concurrent segments while the sequential kernel's grid
+    // (E / 64 x S CTAs) would leave resident slots (4 per SM) empty and the segments stay >= 512 steps long.  (Measured:
+    // with shorter segments the two extra passes cost more than the parallelism returns -- B = 4, L = 512: 10.9 vs 6.5 ms;
+    // and 512-bp windows, the scoring workload, keep the property that a window scores the same bits alone or in a batch.)
+    int P = 1;
+    if (h->time_parallel) {
+      const long long ctas = static_cast<long long>((E + kScanCH - 1) / kScanCH) * S, slots = 4LL * h->num_sms;
+      while (P < 32 && ctas * P * 2 <= slots && L % (P * 2) == 0 && L / (P * 2) >= 512 &&
+             static_cast<size_t>(S) * P * 2 * 2 * E * kScanN * sizeof(float) <= kSegStateBytes)
+        P *= 2;
+    }
+    // dt_proj runs inside the scan kernel (tcgen05, scan.cuh) unless the time-parallel passes need delta in memory
+    const bool fuse_dt = h->fuse_dt && P == 1;
     for (int dir = 0; dir < 2; ++dir) {
       {
         StageTimer tm(h, st, PCAD_ST_X_PROJ);
         rc = op_linear(h, ws.xc[dir], lw.dir[dir].x_proj, ws.dbc[dir], T, RP, E, E, E, RP, f32, h->num_sms, st);
         if (rc) return rc;
       }
-      if (!h->fuse_dt) {
+      if (!fuse_dt) {
         StageTimer tm(h, st, PCAD_ST_DT_PROJ);
         rc = op_linear(h, ws.dbc[dir], lw.dir[dir].dt_proj, ws.delta[dir], T, E, R, RP, R, E, f32, h->num_sms, st);
         if (rc) return rc;
@@ -594,27 +607,16 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st, int prune_idx = 
     {
       StageTimer tm(h, st, PCAD_ST_SCAN);
       const uint8_t* zbase = static_cast<const uint8_t*>(ws.xz) + static_cast<size_t>(E) * h->act_size;
-      if (h->fuse_dt)   // dt_proj inside the scan: it reads the x_proj outputs (dt | B | C) and the re-laid dt_proj weights
+      pruned = prune_idx >= 0 && li == h->cfg.n_layer - 1 && P == 1 && h->prune_last && L >= 8;
+      const int Lrun = pruned ? (prune_idx > L - 1 - prune_idx ? prune_idx : L - 1 - prune_idx) + 1 : 0;
+      if (fuse_dt)   // the scan reads the x_proj outputs (dt | B | C) and the dt_proj weights
         rc = op_biscan(h, ws.xc[0], ws.dbc[0], ws.dbc[0], ws.xc[1], ws.dbc[1], ws.dbc[1], RP, R, zbase, 2 * E,
                        lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
-                       st, lw.dir[0].dt_proj_p, lw.dir[1].dt_proj_p);
+                       st, lw.dir[0].dt_proj, lw.dir[1].dt_proj, R, R, 1, nullptr, nullptr, Lrun);
       else {
-        // low batch / long context: cut every sequence into P concurrent segments while the sequential kernel's grid
-        // (E / 64 x S CTAs) would leave resident slots (4 per SM) empty and the segments stay >= 512 steps long.  (Measured:
-        // with shorter segments the two extra passes cost more than the parallelism returns -- B = 4, L = 512: 10.9 vs 6.5 ms;
-        // and 512-bp windows, the scoring workload, keep the property that a window scores the same bits alone or in a batch.)
-        int P = 1;
-        if (h->time_parallel) {
-          const long long ctas = static_cast<long long>((E + kScanCH - 1) / kScanCH) * S, slots = 4LL * h->num_sms;
-          while (P < 32 && ctas * P * 2 <= slots && L % (P * 2) == 0 && L / (P * 2) >= 512 &&
-                 static_cast<size_t>(S) * P * 2 * 2 * E * kScanN * sizeof(float) <= kSegStateBytes)
-            P *= 2;
-        }
-        pruned = prune_idx >= 0 && li == h->cfg.n_layer - 1 && P == 1 && h->prune_last && L >= 8;
-        const int Lrun = pruned ? (prune_idx > L - 1 - prune_idx ? prune_idx : L - 1 - prune_idx) + 1 : 0;
         rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
                        lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st,
-                       nullptr, nullptr, P, ws.seg_state, ws.seg_sumd, Lrun);
+                       nullptr, nullptr, 0, 0, P, ws.seg_state, ws.seg_sumd, Lrun);
         if (P > 1) h->launch_count += 2;
       }
       if (rc) return rc;
@@ -832,7 +834,6 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
       rc |= dev_alloc(h, &dw.conv_b, h->E);
       rc |= A8(&dw.x_proj, static_cast<size_t>(h->RP) * h->E * a);
       rc |= A8(&dw.dt_proj, static_cast<size_t>(h->E) * h->R * a);
-      if (!h->f32) rc |= A8(&dw.dt_proj_p, static_cast<size_t>(h->E) * kScanDtK * 2);
       rc |= dev_alloc(h, &dw.dt_bias, h->E);
       rc |= dev_alloc(h, &dw.A, static_cast<size_t>(h->E) * h->N);
       rc |= dev_alloc(h, &dw.D, h->E);
@@ -1027,16 +1028,6 @@ int pcad_finalize(pcad_handle* h) {
                                                                            static_cast<bf16*>(lw.in_proj_s), rows, h->d);
     CUDA_TRY(h, cudaDeviceSynchronize());
   }
-  if (h->fuse_dt) {
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    const long long n = static_cast<long long>(h->E) * kScanDtK;
-    for (auto& lw : h->layers)
-      for (int dir = 0; dir < 2; ++dir)
-        prep_dt_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(static_cast<const bf16*>(lw.dir[dir].dt_proj), h->R,
-                                                                              static_cast<bf16*>(lw.dir[dir].dt_proj_p), h->E, h->R);
-    CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaDeviceSynchronize());
-  }
   h->finalized = true;
   return PCAD_OK;
 }
@@ -1086,7 +1077,7 @@ int score_core(pcad_handle* h, int B, int L, int token_idx, cudaStream_t st) {
     fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(ws.pos0, B, 0);
     CUDA_TRY(h, cudaGetLastError());
   }
-  const bool prune = h->prune_last && !h->m2 && !h->fuse_dt && h->cfg.n_layer > 0;
+  const bool prune = h->prune_last && !h->m2 && h->cfg.n_layer > 0;
   int rc = run_backbone(h, B, L, st, prune ? token_idx : -1);
   if (rc) return rc;
   if (prune && h->last_pruned) return run_head(h, B, 1, ws.pos0, 1, ws.logits4, st);   // ws.normed is compact [2B, d]
@@ -1236,7 +1227,7 @@ int pcad_score_masked_at(pcad_handle* h, const uint8_t* ids_dev, int token_idx, 
     CUDA_TRY(h, cudaGetLastError());
   }
   // one scored position, the same in every window: the last layer is computed only at the rows the head reads
-  const bool prune = h->prune_last && !h->m2 && !h->fuse_dt && h->cfg.n_layer > 0;
+  const bool prune = h->prune_last && !h->m2 && h->cfg.n_layer > 0;
   rc = run_backbone(h, B, L, st, prune ? token_idx : -1);
   if (rc) return rc;
   if (prune && h->last_pruned) return run_head(h, B, 1, ws.pos0, 1, logits4_dev, st);
@@ -1374,21 +1365,13 @@ int pcad_op_linear_rowscale(const void* A, const void* W, const float* sumsq_in,
   return op_fail_to_global(op_linear(op_scratch(), A, W, C, M, N, K, lda, ldw, ldc, false, op_num_sms(), static_cast<cudaStream_t>(stream), kEpiRowScale, ep));
 }
 
-int pcad_op_prep_dt_weight(const void* W, int64_t ldw, void* out, int E, int R, void* stream) {
-  if (!W || !out || E <= 0 || R <= 0 || R > kScanDtK || ldw < R) return PCAD_ERR_INVALID;
-  const long long n = static_cast<long long>(E) * kScanDtK;
-  prep_dt_weight_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(W), ldw, static_cast<bf16*>(out), E, R);
-  return cudaGetLastError() == cudaSuccess ? PCAD_OK : PCAD_ERR_CUDA;
-}
-
 int pcad_op_biscan_dt(const void* u_f, const void* dbc_f, const void* u_r, const void* dbc_r, int64_t ldbc, int bc_off,
-                      const void* wdt_f, const void* wdt_r, const void* z, int64_t ldz, const float* A_f, const float* D_f,
-                      const float* dt_bias_f, const float* A_r, const float* D_r, const float* dt_bias_r, void* y, int S, int L, int E,
-                      void* stream) {
+                      const void* wdt_f, const void* wdt_r, int64_t ldw, int R, const void* z, int64_t ldz, const float* A_f,
+                      const float* D_f, const float* dt_bias_f, const float* A_r, const float* D_r, const float* dt_bias_r, void* y,
+                      int S, int L, int E, void* stream) {
   if (!wdt_f || !wdt_r) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_biscan(op_scratch(), u_f, dbc_f, dbc_f, u_r, dbc_r, dbc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
-                                     A_r, D_r, dt_bias_r, y, S, L, E, false, static_cast<cudaStream_t>(stream), wdt_f, wdt_r));
+                                     A_r, D_r, dt_bias_r, y, S, L, E, false, static_cast<cudaStream_t>(stream), wdt_f, wdt_r, ldw, R));
 }
 
 int pcad_op_add_rmsnorm(const void* x, const void* res_in, const float* w, void* y, void* res_out, int64_t rows, int d, float eps, int dtype, int res_dtype, void* stream) {
@@ -1417,7 +1400,7 @@ int pcad_op_biscan_segmented(const void* u_f, const void* delta_f, const void* b
   if (dtype != PCAD_BF16 && dtype != PCAD_F32) return PCAD_ERR_INVALID;
   return op_fail_to_global(op_biscan(op_scratch(), u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, dt_bias_f,
                                      A_r, D_r, dt_bias_r, y, S, L, E, dtype == PCAD_F32, static_cast<cudaStream_t>(stream), nullptr,
-                                     nullptr, segments, seg_state, seg_sumd));
+                                     nullptr, 0, 0, segments, seg_state, seg_sumd));
 }
 
 int pcad_op_ssd_scan(const void* xbc_f, const void* xbc_r, int64_t ld_xbc, const void* dt_raw, int64_t ld_dt, const float* A_f,

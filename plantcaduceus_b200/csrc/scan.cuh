@@ -73,13 +73,12 @@ constexpr int kScanUnroll = PCAD_SCAN_UNROLL;   // steps per main-loop block (st
 
 template <int V> struct IntTag { static constexpr int value = V; };
 
-constexpr int kScanDtK = 64;        // FUSEDT: contraction length of the in-kernel dt_proj (dt_rank zero-padded to 64)
-constexpr int kScanDlPitch = 136;   // FUSEDT: row pitch (elements) of the delta tile: 272 B = 68 words -> conflict-free fragment stores
+constexpr int kScanDtK = 64;        // FUSEDT: contraction length of the in-kernel dt_proj (dt_rank zero-padded to 64 by the TMA)
+constexpr int kScanTmemCols = 64;   // FUSEDT: 2 stages x 32 fp32 columns (16 forward steps | 16 reverse-box rows)
 
 // FUSEDT = false: delta arrives ready-made (dt_proj ran as a GEMM).  FUSEDT = true (bf16): the stage carries the
-// rank-R dt rows instead ([16][64] tile, 128-byte swizzled by TMA so that mma A-fragments are read without bank
-// conflicts; it comes first because the swizzle atom needs 1024-byte alignment) and each warp computes its own
-// 16 x 32 delta tile with mma.sync before the main loop.
+// rank-R dt rows of the x_proj outputs instead -- one [32][64] tile (16 forward rows, then the reverse box's 16 rows),
+// 128-byte swizzled by TMA: the B operand of a tcgen05.mma whose A operand is this block's slice of dt_proj.weight.
 template <typename T, bool FUSEDT> struct ScanStage;
 template <typename T>
 struct ScanStage<T, false> {
@@ -89,25 +88,25 @@ struct ScanStage<T, false> {
 };
 template <typename T>
 struct ScanStage<T, true> {
-  T dt[2][kScanTC][kScanDtK];        // x_proj output columns 0..63 (dt | whatever follows: the padded weight zeroes it)
+  T dt[2][kScanTC][kScanDtK];        // x_proj output columns 0..63 (dt | whatever follows: the zero-filled weight columns cancel it)
   T u[2][kScanTC][kScanCH];
-  T bc_raw[2][kScanTC][2 * kScanN];
 };
 
-template <typename T, bool FUSEDT>
-struct ScanShared {
-  ScanStage<T, FUSEDT> st[2];
+template <typename T, bool FUSEDT> struct ScanShared;
+template <typename T>
+struct ScanShared<T, false> {
+  ScanStage<T, false> st[2];
   float bc[2][kScanTC][2 * kScanN];   // fp32 B|C of the chunk being computed
   T pz[2][2][kScanTC][kScanCH];       // [partial | z][direction][step][channel]: prefetched for the chunk epilogue
-  T dl[FUSEDT ? 2 : 1][FUSEDT ? kScanTC : 1][FUSEDT ? kScanDlPitch : 8];   // FUSEDT: delta of the chunk, per direction
 };
-
-// mma.sync m16n8k16, bf16 inputs, fp32 accumulate (row-major A fragment, column-major B fragment)
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
+template <typename T>
+struct ScanShared<T, true> {
+  T wdt[2][kScanCH][kScanDtK];        // dt_proj.weight rows of this block's channels, forward then reverse: 128 x 64, swizzled
+  ScanStage<T, true> st[2];
+  T bc_raw[2][kScanTC][2 * kScanN];   // single-buffered: consumed (converted to fp32) before the next chunk's loads are issued
+  float bc[2][kScanTC][2 * kScanN];
+  T pz[2][2][kScanTC][kScanCH];
+};
 
 // One direction's 16 states of one channel.  step() advances h <- exp(d*A) h + du*B and returns
 // y0 + <C, h>;  bc points at this timestep's fp32 [B(16) | C(16)] row in shared memory (broadcast reads).
@@ -224,42 +223,46 @@ template <> struct ScanDir<false> {
 };
 
 // Staging.  u, delta and B|C of both directions arrive by TMA: six 3-D tensor maps [sequence][row][channel] with a
-// [1][16][128] (B|C: [1][16][32]) box, issued by one thread per chunk into a 2-stage ring and completed on an
-// mbarrier, so the other 255 threads spend no instructions on loads and rows outside [0, L) (ragged last chunk,
+// [1][16][64] (B|C: [1][16][32]) box, issued by one thread per chunk into a 2-stage ring and completed on an
+// mbarrier, so the other threads spend no instructions on loads and rows outside [0, L) (ragged last chunk,
 // either direction) are zero-filled by the hardware.  The reverse direction's box holds ascending rows
 // L-16(c+1) .. L-16c-1, i.e. step j of the chunk sits in box row 15-j.  The parked partials and z rows that the
 // chunk epilogue needs are fetched with cp.async (generic proxy: they were written by this CTA's own st.global).
 //
-// FUSEDT (bf16): tm_df / tm_dr map the x_proj outputs (columns 0..63, 128-byte swizzle) instead of delta, and
-// wdt_f / wdt_r are dt_proj.weight re-laid for the mma B-fragments (prep_dt_weight_kernel): dt_proj
-// [EXT Mamba.dt_proj, F.linear(dt, W)] runs inside the scan, one 16 x 32 x 64 product per warp and chunk, its fp32
-// accumulators rounded to bf16 exactly where the GEMM would have rounded them -- the two dt_proj launches of a layer
-// and the 4 KB per token of delta they write and the scan re-reads disappear.  Measured on B200 (l32, B = 256): the
-// dt_proj stage goes away (-12 ms per step) and the SM clock rises (less HBM traffic under the power cap), but the scan
-// grows by 21 ms (30 with 128-channel blocks): the weight fragments fit neither the registers nor the shared memory
-// that 4 blocks/SM leave, so every chunk re-reads them from L2 and the warp waits out that latency with the MUFU pipe
-// idle (block order does not change it).  Opt-in (PCAD_FUSED_DT=1).
+// FUSEDT (bf16): dt_proj [EXT Mamba.dt_proj, F.linear(dt, W)] runs inside the scan on the tensor core, so the two dt_proj
+// launches of a layer and the 4 KB per token of delta they write and the scan re-reads disappear.  tm_df / tm_dr map the
+// x_proj outputs (columns 0..63, 128-byte swizzle) instead of delta; tm_wf / tm_wr map dt_proj.weight [E, R] (box 64 x 64:
+// columns >= R are zero-filled by the TMA, which also cancels whatever follows dt in the x_proj rows).  The block's 128
+// weight rows (64 forward channels, 64 reverse) stay in shared memory for its whole life as the A operand; per chunk ONE
+// thread issues  D[128 x 32] = W[128 x 64] . dt_tile[32 x 64]^T  (tcgen05.mma, M 128, N 32: 16 forward steps | 16
+// reverse-box rows; the cross terms are wasted, at 0.5 MFLOP per chunk nobody cares) into one of two 32-column TMEM
+// stages, one chunk ahead of the recurrence.  TMEM lane = thread: tcgen05.ld hands every thread the 16 raw delta values of
+// ITS (direction, channel) for the chunk straight into registers -- no shared-memory round trip, one LDS per step less --
+// and they are rounded to bf16 exactly where the GEMM would have rounded them.
 template <typename T, bool PRECISE, bool FUSEDT>
 __global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : (kScanCH == 64 ? PCAD_SCAN_MINBLOCKS64 : PCAD_SCAN_MINBLOCKS))
 biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__ CUtensorMap tm_df,
               const __grid_constant__ CUtensorMap tm_bcf, const __grid_constant__ CUtensorMap tm_ur,
               const __grid_constant__ CUtensorMap tm_dr, const __grid_constant__ CUtensorMap tm_bcr,
-              const T* __restrict__ wdt_f, const T* __restrict__ wdt_r,
+              const __grid_constant__ CUtensorMap tm_wf, const __grid_constant__ CUtensorMap tm_wr, int dt_ksteps,
               const T* __restrict__ z, long long ldz, const float* __restrict__ A_f, const float* __restrict__ D_f,
               const float* __restrict__ bias_f, const float* __restrict__ A_r, const float* __restrict__ D_r,
               const float* __restrict__ bias_r, T* y, int L, int E, const float* __restrict__ h0, int Lrun) {
-  static_assert(!FUSEDT || (sizeof(T) == 2 && !PRECISE), "the in-kernel dt_proj is a bf16-path feature");
-  extern __shared__ __align__(128) uint8_t scan_smem_raw[];
-  // TMA destinations must be 128-byte aligned (1024 for the swizzled dt tiles); the runtime only promises 16 for the
-  // dynamic segment (pointer arithmetic on the array itself, so that the accesses stay in the shared address space)
-  constexpr uint32_t kAlign = FUSEDT ? 1024u : 128u;
+  static_assert(!FUSEDT || (sizeof(T) == 2 && !PRECISE && kScanCH == 64 && kScanTC == 16),
+                "the in-kernel dt_proj is a bf16-path feature of the 64-channel, 16-step kernel");
+  // 1024-byte alignment: the swizzled tiles (TMA destinations, MMA operands) need it; the shared window of a CTA starts at
+  // an aligned address, so the declared alignment is the real one (checked below in the FUSEDT kernel)
+  extern __shared__ __align__(1024) uint8_t scan_smem_raw[];
   typedef ScanShared<T, FUSEDT> Shared;
   typedef ScanStage<T, FUSEDT> Stage;
-  Shared& sm = *reinterpret_cast<Shared*>(scan_smem_raw + ((kAlign - (smem_u32(scan_smem_raw) & (kAlign - 1u))) & (kAlign - 1u)));
+  Shared& sm = *reinterpret_cast<Shared*>(scan_smem_raw);
   // Un-gated outputs of the chunk, per direction.  A separate (static) symbol on purpose: the compiler can then
   // prove that the main loop's stores to it do not alias the loads of later steps and overlaps consecutive steps.
   __shared__ __align__(16) float ys[2][kScanTC][kScanCH];
   __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ __align__(8) uint64_t dt_bar[2];    // FUSEDT: the stage's dt tile has landed (what the MMA issuer waits for)
+  __shared__ __align__(8) uint64_t w_bar;        // FUSEDT: the weight rows have landed
+  __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x;
   const int dir = tid / kScanCH;          // warp-uniform: the first half of the warps runs forward, the second half reverse
@@ -274,16 +277,38 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   const int nch = (Lrun + kScanTC - 1) / kScanTC;
   constexpr int VEC = 16 / sizeof(T);              // elements per 16-byte vector
   constexpr int SEGS = kScanCH / VEC;              // 16-byte segments per 128-channel row
-  constexpr uint32_t kStageBytes = sizeof(Stage);
+  constexpr uint32_t kDtBytes = sizeof(T) * 2 * kScanTC * kScanDtK;
+  constexpr uint32_t kStageBytes = FUSEDT ? sizeof(Stage) - kDtBytes + sizeof(T) * 2 * kScanTC * 2 * kScanN : sizeof(Stage);
 
   if (tid == 0) {
-    mbar_init(&full_bar[0], 1);
-    mbar_init(&full_bar[1], 1);
+    // FUSEDT: a stage is full when its u / B|C loads have landed AND the MMA that turns its dt tile into delta (TMEM) has
+    // completed: the tcgen05.commit is the barrier's second arrival, so the block waits once per chunk
+    mbar_init(&full_bar[0], FUSEDT ? 2 : 1);
+    mbar_init(&full_bar[1], FUSEDT ? 2 : 1);
+    if constexpr (FUSEDT) {
+      if (smem_u32(scan_smem_raw) & 1023u) __trap();
+      mbar_init(&dt_bar[0], 1);
+      mbar_init(&dt_bar[1], 1);
+      mbar_init(&w_bar, 1);
+      tma_prefetch_desc(&tm_wf); tma_prefetch_desc(&tm_wr);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tm_uf); tma_prefetch_desc(&tm_df); tma_prefetch_desc(&tm_bcf);
     tma_prefetch_desc(&tm_ur); tma_prefetch_desc(&tm_dr); tma_prefetch_desc(&tm_bcr);
   }
-  __syncthreads();
+  uint32_t tmem = 0;
+  if constexpr (FUSEDT) {
+    if (tid < 32) {
+      tmem_alloc<kScanTmemCols>(&tmem_slot);
+      tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem = tmem_slot;
+  } else {
+    __syncthreads();
+  }
 
   // chunk c: forward rows 16c .. 16c+15, reverse rows L-16(c+1) .. L-16c-1 (box row 15-j = step j).  One thread.
   auto issue = [&](int c, int stage) {
@@ -292,15 +317,29 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     mbar_arrive_expect_tx(bar, kStageBytes);
     const int rf = c * kScanTC, rr = L - (c + 1) * kScanTC;
     tma_load_3d(&s.u[0][0][0], &tm_uf, bar, e0, rf, seq);
-    tma_load_3d(&s.bc_raw[0][0][0], &tm_bcf, bar, 0, rf, seq);
     tma_load_3d(&s.u[1][0][0], &tm_ur, bar, e0, rr, seq);
-    tma_load_3d(&s.bc_raw[1][0][0], &tm_bcr, bar, 0, rr, seq);
     if constexpr (FUSEDT) {
-      tma_load_3d(&s.dt[0][0][0], &tm_df, bar, 0, rf, seq);
-      tma_load_3d(&s.dt[1][0][0], &tm_dr, bar, 0, rr, seq);
+      tma_load_3d(&sm.bc_raw[0][0][0], &tm_bcf, bar, 0, rf, seq);
+      tma_load_3d(&sm.bc_raw[1][0][0], &tm_bcr, bar, 0, rr, seq);
+      mbar_arrive_expect_tx(&dt_bar[stage], kDtBytes);
+      tma_load_3d(&s.dt[0][0][0], &tm_df, &dt_bar[stage], 0, rf, seq);
+      tma_load_3d(&s.dt[1][0][0], &tm_dr, &dt_bar[stage], 0, rr, seq);
     } else {
+      tma_load_3d(&s.bc_raw[0][0][0], &tm_bcf, bar, 0, rf, seq);
+      tma_load_3d(&s.bc_raw[1][0][0], &tm_bcr, bar, 0, rr, seq);
       tma_load_3d(&s.d[0][0][0], &tm_df, bar, e0, rf, seq);
       tma_load_3d(&s.d[1][0][0], &tm_dr, bar, e0, rr, seq);
+    }
+  };
+  // FUSEDT, one thread: delta of chunk c (its dt tile has landed in `stage`) -> TMEM columns [32 stage, 32 stage + 32)
+  auto issue_dt_mma = [&](int c, int stage) {
+    if constexpr (FUSEDT) {
+      mbar_wait(&dt_bar[stage], (c >> 1) & 1);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 2 * kScanTC);
+      const uint64_t da = make_smem_desc_sw128(smem_u32(&sm.wdt[0][0][0]));
+      const uint64_t db = make_smem_desc_sw128(smem_u32(&sm.st[stage].dt[0][0][0]));
+      umma_bf16_ss_k64_commit(tmem + stage * 2 * kScanTC, da, db, idesc, dt_ksteps, &full_bar[stage]);
     }
   };
 
@@ -315,62 +354,45 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   const float Dskip = active ? (dir ? D_r : D_f)[e] : 0.f;
   const float bscale = ScanDir<PRECISE>::b_scale();
 
-  if (tid == 0) issue(0, 0);
+  if (tid < 32 && elect_one()) {
+    if constexpr (FUSEDT) {
+      mbar_arrive_expect_tx(&w_bar, sizeof(sm.wdt));
+      tma_load_3d(&sm.wdt[0][0][0], &tm_wf, &w_bar, 0, e0, 0);
+      tma_load_3d(&sm.wdt[1][0][0], &tm_wr, &w_bar, 0, e0, 0);
+    }
+    issue(0, 0);
+    if constexpr (FUSEDT) {
+      mbar_wait(&w_bar, 0);
+      issue_dt_mma(0, 0);
+    }
+  }
+  if constexpr (FUSEDT) mbar_wait(&w_bar, 0);   // every later MMA issuer has observed the weight tile's arrival
   for (int c = 0; c < nch; ++c) {
     const int stage = c & 1;
+    // Issue work: TMA by warp 0, the dt_proj MMA by warp 2 (a different scheduler: every instruction of these paths is on the
+    // block's critical path to the next barrier).  Whole warp into the branch, then elect.sync: the compiler then knows a
+    // single lane issues and emits the TMA / MMA instructions back to back instead of one election loop per instruction.
+    const bool tma_warp = tid < 32, mma_warp = (tid >> 5) == 2;
     // every thread is past the barrier that followed chunk c-1's main loop: stage^1 is free to be overwritten
-    if (tid == 0 && c + 1 < nch) issue(c + 1, stage ^ 1);
+    if constexpr (!FUSEDT) {
+      if (tma_warp && c + 1 < nch) {
+        if (elect_one()) issue(c + 1, stage ^ 1);
+      }
+    }
     const Stage& s = sm.st[stage];
     const int i0 = c * kScanTC;
     const int nsteps = min(kScanTC, Lrun - i0);
     const bool has_final = (L - 1 - (i0 + nsteps - 1)) < i0 + nsteps;
     mbar_wait(&full_bar[stage], (c >> 1) & 1);
-    if constexpr (FUSEDT) {
-      // delta[16 rows][this warp's 32 channels] = dt[16][64] x W_dt[32][64]^T.  A-fragments from the swizzled tile
-      // (16-byte chunk c of row r sits at chunk c ^ (r & 7)); B-fragments straight from global / L2 in the
-      // per-lane order prep_dt_weight_kernel left them in (32 contiguous bytes per channel and lane quarter).
-      const int lane = tid & 31, g = lane >> 2, q = lane & 3;
-      const int wch0 = ((tid >> 5) % (kScanCH / 32)) * 32;
-      const uint8_t* dtile = reinterpret_cast<const uint8_t*>(&s.dt[dir][0][0]);
-      uint32_t afr[4][4];
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {          // k half: columns ks*16 + hh*8 + q*2 live in 16-byte chunk ks*2 + hh
-          const int chunk = ks * 2 + hh;
-          afr[ks][hh * 2 + 0] = *reinterpret_cast<const uint32_t*>(dtile + g * 128 + ((chunk ^ g) << 4) + q * 4);
-          afr[ks][hh * 2 + 1] = *reinterpret_cast<const uint32_t*>(dtile + (g + 8) * 128 + ((chunk ^ g) << 4) + q * 4);
-        }
-      }
-      const T* wdt = dir ? wdt_r : wdt_f;
-      T* dlw = &sm.dl[dir][0][0];
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int cch = wch0 + nt * 8 + g;        // channel (within the block's 128) whose weights this lane holds
-        uint4 w0 = make_uint4(0u, 0u, 0u, 0u), w1 = w0;
-        if (e0 + cch < E) {
-          const uint4* wp = reinterpret_cast<const uint4*>(wdt + (static_cast<long long>(e0 + cch) * kScanDtK + q * 16));
-          w0 = __ldg(wp);
-          w1 = __ldg(wp + 1);
-        }
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        mma_bf16_16816(acc, afr[0], w0.x, w0.y);
-        mma_bf16_16816(acc, afr[1], w0.z, w0.w);
-        mma_bf16_16816(acc, afr[2], w1.x, w1.y);
-        mma_bf16_16816(acc, afr[3], w1.z, w1.w);
-        const int col = wch0 + nt * 8 + q * 2;
-        *reinterpret_cast<uint32_t*>(dlw + g * kScanDlPitch + col) = pack_bf16x2(acc[0], acc[1]);
-        *reinterpret_cast<uint32_t*>(dlw + (g + 8) * kScanDlPitch + col) = pack_bf16x2(acc[2], acc[3]);
-      }
-      __syncwarp();   // the warp consumes exactly the 32 channels it produced
-    }
     // B|C to fp32, once per chunk, 4 values per thread (B carries the ln 2 of the log2-domain delta on the fast
     // path); the reverse direction's rows are un-flipped here so that the main loop indexes both alike
 #pragma unroll
     for (int gi = tid; gi < 2 * kScanTC * 2 * kScanN / 4; gi += kScanThreads) {   // 256 groups of 4 values
       const int dd = gi >> 7, r = gi & 127;
       const int j = r >> 3, k0 = (r & 7) * 4;
-      const T* src = &s.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
+      const T* src;
+      if constexpr (FUSEDT) src = &sm.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
+      else src = &s.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
       float4 v;
       if constexpr (sizeof(T) == 2) {
         const uint2 raw = *reinterpret_cast<const uint2*>(src);
@@ -383,6 +405,13 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
       *reinterpret_cast<float4*>(&sm.bc[dd][j][k0]) = v;
     }
     __syncthreads();   // sm.bc is complete; chunk c-1's epilogue (its parked partials, its reads of ys / pz) is done
+    if constexpr (FUSEDT) {
+      // the single B|C landing buffer has been consumed: only now may the next chunk's loads go out (they still have this
+      // chunk's whole main loop to arrive)
+      if (tma_warp && c + 1 < nch) {
+        if (elect_one()) issue(c + 1, stage ^ 1);
+      }
+    }
     // Positions of this chunk that the other direction visited in an EARLIER chunk will be finalised in the
     // epilogue: fetch their parked partials and z rows now (every earlier epilogue is complete and visible after the
     // barrier above), so that the epilogue does not wait on global memory.
@@ -414,6 +443,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     }
     cp_async_commit();
 
+    if constexpr (FUSEDT) tc_fence_after();   // delta of the chunk is in TMEM (the wait on full_bar above covered the MMA)
     if (active) {
       const float* bcp = &sm.bc[dir][0][0];
       float* ysp = &ys[dir][0][ch];
@@ -421,55 +451,112 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
         constexpr bool REV = decltype(rev_tag)::value != 0;   // compile-time row order: immediate offsets in the unrolled loop
         const T* up = &s.u[REV ? 1 : 0][0][ch];
         auto row = [](int j) { return (REV ? kScanTC - 1 - j : j) * kScanCH; };
-        auto drow = [](int j) { return (REV ? kScanTC - 1 - j : j) * (FUSEDT ? kScanDlPitch : kScanCH); };
-        const T* dp;
-        if constexpr (FUSEDT) dp = &sm.dl[REV ? 1 : 0][0][ch];
-        else dp = &s.d[REV ? 1 : 0][0][ch];
-        // softplus runs one step ahead of the recurrence, so its LDS -> EX2 -> polynomial latency chain is off the
+        // softplus runs one step ahead of the recurrence, so its load -> EX2 -> polynomial latency chain is off the
         // critical path of the step that consumes it
         float uu = ActT<T>::to_f(up[row(0)]);
         float dl;
-        {
-          const float draw = ActT<T>::to_f(dp[drow(0)]);
-          dl = S.delta(draw);
-        }
-        auto advance = [&](int j) -> float {
-          const int jn = min(j + 1, kScanTC - 1);
+        // one step: consumes (uu, dl) prepared by the previous call, prepares the next from row jn and the raw delta draw_n
+        auto advance = [&](int j, int jn, float draw_n) -> float {
           const float uu_n = ActT<T>::to_f(up[row(jn)]);
-          const float draw_n = ActT<T>::to_f(dp[drow(jn)]);
           const float dl_n = S.delta(draw_n);
           const float yv = S.step(dl, dl * uu, Dskip * uu, bcp + j * 2 * kScanN);
           uu = uu_n;
           dl = dl_n;
           return yv;
         };
-        // blocks of kScanUnroll steps with the stores deferred to the end of the block: no shared-memory store sits
-        // between the loads of consecutive steps, so the scheduler overlaps one step's tail with the next step's head
-        int j = 0;
+        if constexpr (FUSEDT) {
+          // this thread's TMEM lane holds delta of its channel: columns 0..15 forward steps, 16..31 the reverse box's rows
+          // (step j = row 15 - j).  Kept as 8 bf16 pairs in STEP order: pair q = steps 2q (low half), 2q + 1 (high half).
+          const uint32_t tmem_dl = tmem + (static_cast<uint32_t>((tid >> 5) * 32) << 16) + stage * 2 * kScanTC + (REV ? kScanTC : 0);
+          uint32_t dp2[kScanTC / 2 + 1];
+          {
+            uint32_t dr[kScanTC];
+            tmem_ld_32x32b_x16(tmem_dl, dr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < kScanTC / 2; ++q) {
+              const int c0 = REV ? kScanTC - 1 - 2 * q : 2 * q, c1 = REV ? kScanTC - 2 - 2 * q : 2 * q + 1;
+              dp2[q] = pack_bf16x2(__uint_as_float(dr[c0]), __uint_as_float(dr[c1]));
+            }
+            dp2[kScanTC / 2] = 0u;
+          }
+          auto lo = [](uint32_t w) { return __uint_as_float(w << 16); };
+          auto hi = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
+          dl = S.delta(lo(dp2[0]));
+          int j = 0;
+          // blocks of kScanUnroll steps reading a 5-pair window that slides by 4 pairs per block: one loop body
+          uint32_t w[kScanUnroll / 2 + 1];
+#pragma unroll
+          for (int q = 0; q <= kScanUnroll / 2; ++q) w[q] = dp2[q];
+          static_assert(kScanUnroll == 8, "the window logic below is written for 8-step blocks");
 #pragma unroll 1
-        for (; j + kScanUnroll <= nsteps; j += kScanUnroll) {
-          float yv[kScanUnroll];
+          for (; j + kScanUnroll <= nsteps; j += kScanUnroll) {
+            float yv[kScanUnroll];
 #pragma unroll
-          for (int k = 0; k < kScanUnroll; ++k) yv[k] = advance(j + k);
+            for (int k = 0; k < kScanUnroll; ++k) {
+              const uint32_t wn = w[(k + 1) >> 1];
+              yv[k] = advance(j + k, min(j + k + 1, kScanTC - 1), ((k + 1) & 1) ? hi(wn) : lo(wn));
+            }
 #pragma unroll
-          for (int k = 0; k < kScanUnroll; ++k) ysp[(j + k) * kScanCH] = yv[k];
+            for (int k = 0; k < kScanUnroll; ++k) ysp[(j + k) * kScanCH] = yv[k];
+#pragma unroll
+            for (int q = 0; q <= kScanUnroll / 2; ++q) w[q] = dp2[min(q + kScanUnroll / 2, kScanTC / 2)];
+          }
+          // ragged last chunk: single steps, the next raw value re-read from TMEM (a dynamic column is an address there)
+#pragma unroll 1
+          for (; j < nsteps; ++j) {
+            const int jn = min(j + 1, kScanTC - 1);
+            const uint32_t rn = tmem_ld_32x32b_x1(tmem_dl + (REV ? kScanTC - 1 - jn : jn));
+            tmem_ld_wait();
+            ysp[j * kScanCH] = advance(j, jn, lo(pack_bf16x2(__uint_as_float(rn), 0.f)));
+          }
+        } else {
+          const T* dp = &s.d[REV ? 1 : 0][0][ch];
+          dl = S.delta(ActT<T>::to_f(dp[row(0)]));
+          // blocks of kScanUnroll steps with the stores deferred to the end of the block: no shared-memory store sits
+          // between the loads of consecutive steps, so the scheduler overlaps one step's tail with the next step's head
+          int j = 0;
+#pragma unroll 1
+          for (; j + kScanUnroll <= nsteps; j += kScanUnroll) {
+            float yv[kScanUnroll];
+#pragma unroll
+            for (int k = 0; k < kScanUnroll; ++k) {
+              const int jn = min(j + k + 1, kScanTC - 1);
+              yv[k] = advance(j + k, jn, ActT<T>::to_f(dp[row(jn)]));
+            }
+#pragma unroll
+            for (int k = 0; k < kScanUnroll; ++k) ysp[(j + k) * kScanCH] = yv[k];
+          }
+#pragma unroll 1
+          for (; j < nsteps; ++j) {
+            const int jn = min(j + 1, kScanTC - 1);
+            ysp[j * kScanCH] = advance(j, jn, ActT<T>::to_f(dp[row(jn)]));
+          }
         }
-#pragma unroll 1
-        for (; j < nsteps; ++j) ysp[j * kScanCH] = advance(j);
       };
       if (dir) run_chunk(IntTag<1>());
       else run_chunk(IntTag<0>());
+    }
+    if constexpr (FUSEDT) {
+      tc_fence_before();   // this chunk's TMEM reads are ordered before the barrier below (the stage is rewritten two MMAs on)
+      // next chunk's delta: its dt tile was requested a whole main loop ago; the TMEM stage it writes was last read in
+      // chunk c-1, behind two block barriers
+      if (mma_warp && c + 1 < nch) {
+        if (elect_one()) issue_dt_mma(c + 1, stage ^ 1);
+      }
     }
     cp_async_wait<0>();
     __syncthreads();   // both directions' un-gated outputs of the chunk are in ys, partials / z in sm.pz
 
     // ---- chunk epilogue: 16-byte vectors; item = (direction, step, segment of VEC channels)
+    bool fast_done = false;
     if constexpr (!PRECISE && sizeof(T) == 2) {
       // bf16 fast paths for the two block-uniform cases (every chunk of an even-length sequence): all items of
       // the chunk park ("early": the other direction comes in a later chunk) or all finalise from a partial parked
       // in an earlier chunk ("late").  No per-item branching, packed fp32x2 arithmetic for the add and the gate.
       const bool early = !has_final, late = late_chunk;
       if (early || late) {
+        fast_done = true;
         static_assert(kScanTC * kScanSeg8 == kScanThreads, "one item per thread and direction");
         const int j = tid / kScanSeg8, seg = tid % kScanSeg8;
         const int chn = e0 + seg * 8;
@@ -506,9 +593,9 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
             *reinterpret_cast<uint4*>(y + (row0 + t) * E + chn) = out;
           }
         }
-        continue;
       }
     }
+    if (fast_done) continue;
     for (int idx = tid; idx < 2 * kScanTC * SEGS; idx += kScanThreads) {
       const int dd = idx / (kScanTC * SEGS);
       const int rem = idx - dd * (kScanTC * SEGS);
@@ -545,51 +632,49 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     // no barrier here: the next iteration's first __syncthreads orders these reads of sm.ys and of the stage
     // against their next writers
   }
-}
-
-// dt_proj.weight [E, R] (row pitch ldw) -> [E, 64] in the order the FUSEDT kernel's mma B-fragments are read: for lane
-// quarter q, k-step ks, half h, element e:  out[c][q*16 + ks*4 + h*2 + e] = W[c][ks*16 + h*8 + q*2 + e]  (0 for k >= R).
-__global__ void prep_dt_weight_kernel(const bf16* __restrict__ W, long long ldw, bf16* __restrict__ out, int E, int R) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(E) * kScanDtK) return;
-  const int c = static_cast<int>(idx / kScanDtK), o = static_cast<int>(idx % kScanDtK);
-  const int q = o >> 4, ks = (o >> 2) & 3, hh = (o >> 1) & 1, e = o & 1;
-  const int k = ks * 16 + hh * 8 + q * 2 + e;
-  out[idx] = k < R ? W[c * ldw + k] : __float2bfloat16(0.f);
+  if constexpr (FUSEDT) {
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc<kScanTmemCols>(tmem);
+  }
 }
 
 // FUSEDT = true: delta_f / delta_r are the x_proj outputs ([S*L, ldbc], dt in columns 0..R-1, ldbc >= 64) and wdt_f / wdt_r
-// the weights from prep_dt_weight_kernel; otherwise delta_* are [S*L, E] and wdt_* unused.
+// the dt_proj weights [E, R] (row pitch ldw, a multiple of 8 elements; R <= 64); otherwise delta_* are [S*L, E] and wdt_* unused.
 template <typename T, bool PRECISE, bool FUSEDT = false>
 inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, const T* u_r, const T* delta_r,
                                  const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
                                  const float* D_r, const float* bias_r, T* y, int S, int L, int E,
-                                 cudaStream_t stream, const T* wdt_f = nullptr, const T* wdt_r = nullptr,
-                                 const float* h0 = nullptr, int Lrun = 0) {
-  size_t smem = sizeof(ScanShared<T, FUSEDT>) + (FUSEDT ? 1024 : 128);   // + alignment slack for the TMA destinations
+                                 cudaStream_t stream, const T* wdt_f = nullptr, const T* wdt_r = nullptr, long long ldw = 0,
+                                 int R = 0, const float* h0 = nullptr, int Lrun = 0) {
+  size_t smem = sizeof(ScanShared<T, FUSEDT>);
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static unsigned long long attr_done = 0;
   cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, FUSEDT>, static_cast<int>(smem), attr_done);
   if (e1 != cudaSuccess) return e1;
   constexpr bool f32 = sizeof(T) == 4;
-  CUtensorMap tm[6];
+  CUtensorMap tm[8];
   bool ok = make_tmap_3d(&tm[0], f32, u_f, E, L, S, E, kScanCH, kScanTC) && make_tmap_3d(&tm[2], f32, u_r, E, L, S, E, kScanCH, kScanTC);
   if (FUSEDT) {
-    if (ldbc < kScanDtK || !wdt_f || !wdt_r) return cudaErrorInvalidValue;
+    if (ldbc < kScanDtK || !wdt_f || !wdt_r || R <= 0 || R > kScanDtK || ldw < R || (ldw % 8)) return cudaErrorInvalidValue;
     ok = ok && make_tmap_3d(&tm[1], f32, delta_f, ldbc, L, S, ldbc, kScanDtK, kScanTC, true) &&
          make_tmap_3d(&tm[3], f32, delta_r, ldbc, L, S, ldbc, kScanDtK, kScanTC, true);
+    ok = ok && make_tmap_3d(&tm[6], f32, wdt_f, R, E, 1, ldw, kScanDtK, kScanCH, true) &&
+         make_tmap_3d(&tm[7], f32, wdt_r, R, E, 1, ldw, kScanDtK, kScanCH, true);
   } else {
     ok = ok && make_tmap_3d(&tm[1], f32, delta_f, E, L, S, E, kScanCH, kScanTC) &&
          make_tmap_3d(&tm[3], f32, delta_r, E, L, S, E, kScanCH, kScanTC);
+    tm[6] = tm[0];
+    tm[7] = tm[0];
   }
   ok = ok && make_tmap_3d(&tm[4], f32, bc_f + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
   ok = ok && make_tmap_3d(&tm[5], f32, bc_r + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
   if (!ok) return cudaErrorInvalidValue;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
   biscan_kernel<T, PRECISE, FUSEDT><<<grid, kScanThreads, smem, stream>>>(
-      tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], wdt_f, wdt_r, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E, h0,
-      (Lrun > 0 && Lrun < L) ? Lrun : L);
+      tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], tm[6], tm[7], (R + 15) / 16, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E,
+      h0, (Lrun > 0 && Lrun < L) ? Lrun : L);
   return cudaGetLastError();
 }
 
@@ -709,7 +794,7 @@ inline cudaError_t launch_biscan_time_parallel(const T* u_f, const T* delta_f, c
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   return launch_biscan<T, PRECISE, false>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, bias_f, A_r, D_r,
-                                          bias_r, y, S * P, Lseg, E, stream, nullptr, nullptr, state);
+                                          bias_r, y, S * P, Lseg, E, stream, nullptr, nullptr, 0, 0, state);
 }
 
 }  // namespace pcad

@@ -31,7 +31,7 @@ def test_header_and_binding_agree(lib):
     assert sorted(_lib.EXPORTS) == syms, (set(syms) ^ set(_lib.EXPORTS))
     for s in syms:
         assert hasattr(lib, s), f"libpcad.so does not export {s}"
-    assert lib.pcad_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.pcad_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_no_cpu_fallback(lib):
