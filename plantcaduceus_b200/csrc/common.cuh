@@ -253,6 +253,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// mbarrier wait that traps instead of spinning forever if a phase never completes (a wrong descriptor or byte count would
+// otherwise hang the GPU; ~2^28 polls is seconds, far beyond any legitimate wait)
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 28); ++i)
+    if (mbar_try_wait(bar, parity)) return;
+  asm volatile("trap;");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

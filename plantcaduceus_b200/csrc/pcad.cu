@@ -61,6 +61,7 @@ struct Workspace {
   float* sumsq[2] = {nullptr, nullptr};  // [T, parts] per-column-tile sums of squares of the residual stream (fused-norm path)
   float* seg_state = nullptr;  // time-parallel scan: [S*P, 2, E, 16] segment states
   float* seg_sumd = nullptr;   // time-parallel scan: [S*P, 2, E] sums of delta
+  float* bcf = nullptr;        // Mamba-1 bf16: fp32 [B ln 2 | C] rows of both directions, [2][T][32] (scan.cuh kScanBcF32)
   uint8_t* ascii = nullptr;    // [B, L] staging for the host entry
   float* logits4 = nullptr;    // [B, 4] staging for the host entry
   int* pos = nullptr;          // [B] staging for the host entry
@@ -79,6 +80,7 @@ struct pcad_handle {
   int H = 0, CD = 0, DIP = 0, DIPP = 0;   // Mamba-2: heads, conv channels (x|B|C), in_proj width (z|x|B|C|dt) and its padded pitch
   bool f32 = false;
   bool fuse_dt = false;                // bf16: dt_proj computed inside the scan (tcgen05), no dt_proj launches, no delta in HBM
+  bool bc_f32 = true;                  // bf16: B|C converted to fp32 rows once (bc_to_f32_kernel), scan in its one-barrier mode
   bool fuse_norm = false;   // bf16 activations + bf16 residual: add+RMSNorm folded into the out_proj / in_proj epilogues
   size_t act_size = 2;
   bool finalized = false;
@@ -323,7 +325,7 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
               const float* A_f, const float* D_f, const float* bias_f, const float* A_r, const float* D_r,
               const float* bias_r, void* y, int S, int L, int E, bool f32, cudaStream_t st,
               const void* wdt_f = nullptr, const void* wdt_r = nullptr, long long ldw = 0, int R = 0, int segments = 1,
-              float* seg_state = nullptr, float* seg_sumd = nullptr, int Lrun = 0) {
+              float* seg_state = nullptr, float* seg_sumd = nullptr, int Lrun = 0, float* bcf = nullptr) {
   const int vec = f32 ? 4 : 8;
   if (E % vec || ldbc % vec || bc_off % vec || ldz % vec)
     return fail(h, PCAD_ERR_INVALID, "biscan: E, ldbc, bc_off, ldz must be multiples of %d elements", vec);
@@ -335,23 +337,36 @@ int op_biscan(pcad_handle* h, const void* u_f, const void* delta_f, const void* 
       static_cast<const TT*>(delta_r), static_cast<const TT*>(bc_r), ldbc, bc_off, static_cast<const TT*>(z), ldz, A_f, D_f, \
       bias_f, A_r, D_r, bias_r, static_cast<TT*>(y), S, L, E
   const bool fused_dt = wdt_f != nullptr || wdt_r != nullptr;
+  // bcf (bf16, not fused): scratch for float [2][S*L][32]; B|C are converted once here and the scan runs its one-barrier mode
+  const float* bcf_f = nullptr;
+  const float* bcf_r = nullptr;
+  if (bcf && !f32 && !fused_dt) {
+    const long long rows = static_cast<long long>(S) * L;
+    bc_to_f32_kernel<<<static_cast<unsigned>((rows * 8 + 255) / 256), 256, 0, st>>>(static_cast<const bf16*>(bc_f), static_cast<const bf16*>(bc_r),
+                                                                                  ldbc, bc_off, bcf, rows);
+    CUDA_TRY(h, cudaGetLastError());
+    bcf_f = bcf;
+    bcf_r = bcf + rows * 2 * kScanN;
+  }
   if (segments > 1) {   // time-parallel: `segments` concurrent segments per sequence (scan.cuh)
     if (fused_dt || !seg_state || !seg_sumd || L % segments || static_cast<long long>(S) * segments > 65535)
       return fail(h, PCAD_ERR_INVALID, "biscan: the time-parallel scan needs L %% segments == 0, S * segments <= 65535 and its state buffers");
     if (f32) e = launch_biscan_time_parallel<float, true>(PCAD_SCAN_ARGS(float), segments, seg_state, seg_sumd, st);
-    else e = launch_biscan_time_parallel<bf16, false>(PCAD_SCAN_ARGS(bf16), segments, seg_state, seg_sumd, st);
+    else e = launch_biscan_time_parallel<bf16, false>(PCAD_SCAN_ARGS(bf16), segments, seg_state, seg_sumd, st, bcf_f, bcf_r);
     CUDA_TRY(h, e);
     return PCAD_OK;
   }
   if (fused_dt) {   // delta_* are the x_proj outputs, dt_proj runs inside the kernel (tcgen05)
     if (f32 || !wdt_f || !wdt_r || ldbc < kScanDtK || R <= 0 || R > kScanDtK || ldw < R || ldw % 8)
       return fail(h, PCAD_ERR_INVALID, "biscan: the in-kernel dt_proj needs bf16, both weights (R <= 64, row pitch a multiple of 8) and ldbc >= 64");
-    e = launch_biscan<bf16, false, true>(PCAD_SCAN_ARGS(bf16), st, static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r), ldw, R,
-                                         nullptr, Lrun);
+    e = launch_biscan<bf16, false, kScanFusedDt>(PCAD_SCAN_ARGS(bf16), st, static_cast<const bf16*>(wdt_f), static_cast<const bf16*>(wdt_r),
+                                                 ldw, R, nullptr, Lrun);
   } else if (f32) {
-    e = launch_biscan<float, true, false>(PCAD_SCAN_ARGS(float), st, nullptr, nullptr, 0, 0, nullptr, Lrun);
+    e = launch_biscan<float, true, kScanPlain>(PCAD_SCAN_ARGS(float), st, nullptr, nullptr, 0, 0, nullptr, Lrun);
+  } else if (bcf_f) {
+    e = launch_biscan<bf16, false, kScanBcF32>(PCAD_SCAN_ARGS(bf16), st, nullptr, nullptr, 0, 0, nullptr, Lrun, bcf_f, bcf_r);
   } else {
-    e = launch_biscan<bf16, false, false>(PCAD_SCAN_ARGS(bf16), st, nullptr, nullptr, 0, 0, nullptr, Lrun);
+    e = launch_biscan<bf16, false, kScanPlain>(PCAD_SCAN_ARGS(bf16), st, nullptr, nullptr, 0, 0, nullptr, Lrun);
   }
 #undef PCAD_SCAN_ARGS
   CUDA_TRY(h, e);
@@ -382,6 +397,7 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
   const size_t ss_parts = static_cast<size_t>(gemm_sumsq_parts(h->d));
   const size_t o_ss0 = take(T * ss_parts * sizeof(float)), o_ss1 = take(T * ss_parts * sizeof(float));
   const size_t o_segs = take(h->m2 ? 0 : kSegStateBytes), o_segd = take(h->m2 ? 0 : kSegStateBytes / 16);
+  const size_t o_bcf = take((h->m2 || h->f32) ? 0 : T * 2 * 2 * kScanN * sizeof(float));   // fp32 [B ln 2 | C] rows, both directions
   const size_t o_ascii = take(static_cast<size_t>(B) * L);
   const size_t o_l4 = take(static_cast<size_t>(B) * 4 * sizeof(float));
   const size_t o_pos = take(static_cast<size_t>(B) * sizeof(int));
@@ -393,6 +409,7 @@ size_t workspace_layout(const pcad_handle* h, int B, int L, Workspace* ws) {
     ws->delta[0] = p + o_dl0; ws->delta[1] = p + o_dl1; ws->y = p + o_y;
     ws->sumsq[0] = reinterpret_cast<float*>(p + o_ss0); ws->sumsq[1] = reinterpret_cast<float*>(p + o_ss1);
     ws->seg_state = reinterpret_cast<float*>(p + o_segs); ws->seg_sumd = reinterpret_cast<float*>(p + o_segd);
+    ws->bcf = (h->m2 || h->f32) ? nullptr : reinterpret_cast<float*>(p + o_bcf);
     ws->ascii = p + o_ascii; ws->logits4 = reinterpret_cast<float*>(p + o_l4); ws->pos = reinterpret_cast<int*>(p + o_pos);
     ws->pos0 = reinterpret_cast<int*>(p + o_pos0);
   }
@@ -616,8 +633,9 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st, int prune_idx = 
       else {
         rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
                        lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st,
-                       nullptr, nullptr, 0, 0, P, ws.seg_state, ws.seg_sumd, Lrun);
+                       nullptr, nullptr, 0, 0, P, ws.seg_state, ws.seg_sumd, Lrun, h->bc_f32 ? ws.bcf : nullptr);
         if (P > 1) h->launch_count += 2;
+        if (h->bc_f32 && !f32) h->launch_count += 1;
       }
       if (rc) return rc;
     }
@@ -783,6 +801,7 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   h->fuse_dt = false;
   if (const char* fd = getenv("PCAD_FUSED_DT"))
     h->fuse_dt = fd[0] == '1' && !m2 && !h->f32 && h->RP >= kScanDtK && h->R <= kScanDtK && (h->E % 8) == 0;
+  if (const char* bq = getenv("PCAD_SCAN_BC_F32")) h->bc_f32 = bq[0] != '0';   // A/B switch
   if (const char* pl = getenv("PCAD_NO_PRUNE")) h->prune_last = pl[0] != '1';
   if (const char* tp = getenv("PCAD_NO_TIME_PARALLEL")) h->time_parallel = tp[0] != '1';
   if (const char* ng = getenv("PCAD_NO_GRAPH")) h->use_graphs = ng[0] != '1';

@@ -76,35 +76,52 @@ template <int V> struct IntTag { static constexpr int value = V; };
 constexpr int kScanDtK = 64;        // FUSEDT: contraction length of the in-kernel dt_proj (dt_rank zero-padded to 64 by the TMA)
 constexpr int kScanTmemCols = 64;   // FUSEDT: 2 stages x 32 fp32 columns (16 forward steps | 16 reverse-box rows)
 
-// FUSEDT = false: delta arrives ready-made (dt_proj ran as a GEMM).  FUSEDT = true (bf16): the stage carries the
-// rank-R dt rows of the x_proj outputs instead -- one [32][64] tile (16 forward rows, then the reverse box's 16 rows),
-// 128-byte swizzled by TMA: the B operand of a tcgen05.mma whose A operand is this block's slice of dt_proj.weight.
-template <typename T, bool FUSEDT> struct ScanStage;
+// Kernel modes.
+//   kScanPlain: delta arrives ready-made (dt_proj ran as a GEMM), B|C arrive as activations and are converted to fp32 in the
+//     kernel, once per chunk, behind a block barrier (the fp32 parity path and the operator API).
+//   kScanBcF32 (bf16, what the forward runs): B|C arrive as fp32 rows (B already scaled by ln 2: bc_to_f32_kernel), delivered by
+//     TMA like everything else -- no conversion pass, and with the chunk outputs double-buffered ONE block barrier per chunk.
+//   kScanFusedDt (bf16): the stage carries the rank-R dt rows of the x_proj outputs instead of delta -- one [32][64] tile (16
+//     forward rows, then the reverse box's 16 rows), 128-byte swizzled by TMA: the B operand of a tcgen05.mma whose A operand is
+//     this block's slice of dt_proj.weight.
+constexpr int kScanPlain = 0, kScanFusedDt = 1, kScanBcF32 = 2;
+template <typename T, int MODE> struct ScanStage;
 template <typename T>
-struct ScanStage<T, false> {
+struct ScanStage<T, kScanPlain> {
   T u[2][kScanTC][kScanCH];          // [direction][step][channel]
   T d[2][kScanTC][kScanCH];
   T bc_raw[2][kScanTC][2 * kScanN];
 };
 template <typename T>
-struct ScanStage<T, true> {
+struct ScanStage<T, kScanFusedDt> {
   T dt[2][kScanTC][kScanDtK];        // x_proj output columns 0..63 (dt | whatever follows: the zero-filled weight columns cancel it)
   T u[2][kScanTC][kScanCH];
 };
-
-template <typename T, bool FUSEDT> struct ScanShared;
 template <typename T>
-struct ScanShared<T, false> {
-  ScanStage<T, false> st[2];
+struct ScanStage<T, kScanBcF32> {
+  T u[2][kScanTC][kScanCH];
+  T d[2][kScanTC][kScanCH];
+  float bc[2][kScanTC][2 * kScanN];   // fp32 [B ln 2 | C] rows as the TMA delivered them (reverse direction: box row 15 - j = step j)
+};
+
+template <typename T, int MODE> struct ScanShared;
+template <typename T>
+struct ScanShared<T, kScanPlain> {
+  ScanStage<T, kScanPlain> st[2];
   float bc[2][kScanTC][2 * kScanN];   // fp32 B|C of the chunk being computed
   T pz[2][2][kScanTC][kScanCH];       // [partial | z][direction][step][channel]: prefetched for the chunk epilogue
 };
 template <typename T>
-struct ScanShared<T, true> {
+struct ScanShared<T, kScanFusedDt> {
   T wdt[2][kScanCH][kScanDtK];        // dt_proj.weight rows of this block's channels, forward then reverse: 128 x 64, swizzled
-  ScanStage<T, true> st[2];
+  ScanStage<T, kScanFusedDt> st[2];
   T bc_raw[2][kScanTC][2 * kScanN];   // single-buffered: consumed (converted to fp32) before the next chunk's loads are issued
   float bc[2][kScanTC][2 * kScanN];
+  T pz[2][2][kScanTC][kScanCH];
+};
+template <typename T>
+struct ScanShared<T, kScanBcF32> {
+  ScanStage<T, kScanBcF32> st[2];
   T pz[2][2][kScanTC][kScanCH];
 };
 
@@ -239,7 +256,7 @@ template <> struct ScanDir<false> {
 // stages, one chunk ahead of the recurrence.  TMEM lane = thread: tcgen05.ld hands every thread the 16 raw delta values of
 // ITS (direction, channel) for the chunk straight into registers -- no shared-memory round trip, one LDS per step less --
 // and they are rounded to bf16 exactly where the GEMM would have rounded them.
-template <typename T, bool PRECISE, bool FUSEDT>
+template <typename T, bool PRECISE, int MODE>
 __global__ void __launch_bounds__(kScanThreads, PRECISE ? 1 : (kScanCH == 64 ? PCAD_SCAN_MINBLOCKS64 : PCAD_SCAN_MINBLOCKS))
 biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__ CUtensorMap tm_df,
               const __grid_constant__ CUtensorMap tm_bcf, const __grid_constant__ CUtensorMap tm_ur,
@@ -248,17 +265,19 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
               const T* __restrict__ z, long long ldz, const float* __restrict__ A_f, const float* __restrict__ D_f,
               const float* __restrict__ bias_f, const float* __restrict__ A_r, const float* __restrict__ D_r,
               const float* __restrict__ bias_r, T* y, int L, int E, const float* __restrict__ h0, int Lrun) {
-  static_assert(!FUSEDT || (sizeof(T) == 2 && !PRECISE && kScanCH == 64 && kScanTC == 16),
-                "the in-kernel dt_proj is a bf16-path feature of the 64-channel, 16-step kernel");
+  constexpr bool FUSEDT = MODE == kScanFusedDt, BCF32 = MODE == kScanBcF32;
+  static_assert(MODE == kScanPlain || (sizeof(T) == 2 && !PRECISE && kScanCH == 64 && kScanTC == 16),
+                "the in-kernel dt_proj and the fp32 B|C rows are bf16-path features of the 64-channel, 16-step kernel");
   // 1024-byte alignment: the swizzled tiles (TMA destinations, MMA operands) need it; the shared window of a CTA starts at
   // an aligned address, so the declared alignment is the real one (checked below in the FUSEDT kernel)
   extern __shared__ __align__(1024) uint8_t scan_smem_raw[];
-  typedef ScanShared<T, FUSEDT> Shared;
-  typedef ScanStage<T, FUSEDT> Stage;
+  typedef ScanShared<T, MODE> Shared;
+  typedef ScanStage<T, MODE> Stage;
   Shared& sm = *reinterpret_cast<Shared*>(scan_smem_raw);
   // Un-gated outputs of the chunk, per direction.  A separate (static) symbol on purpose: the compiler can then
   // prove that the main loop's stores to it do not alias the loads of later steps and overlaps consecutive steps.
-  __shared__ __align__(16) float ys[2][kScanTC][kScanCH];
+  // kScanBcF32: two buffers (chunk parity), so that a chunk's main loop never writes what the previous chunk's epilogue reads.
+  __shared__ __align__(16) float ys_all[BCF32 ? 2 : 1][2][kScanTC][kScanCH];
   __shared__ __align__(8) uint64_t full_bar[2];
   __shared__ __align__(8) uint64_t dt_bar[2];    // FUSEDT: the stage's dt tile has landed (what the MMA issuer waits for)
   __shared__ __align__(8) uint64_t w_bar;        // FUSEDT: the weight rows have landed
@@ -325,8 +344,13 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
       tma_load_3d(&s.dt[0][0][0], &tm_df, &dt_bar[stage], 0, rf, seq);
       tma_load_3d(&s.dt[1][0][0], &tm_dr, &dt_bar[stage], 0, rr, seq);
     } else {
-      tma_load_3d(&s.bc_raw[0][0][0], &tm_bcf, bar, 0, rf, seq);
-      tma_load_3d(&s.bc_raw[1][0][0], &tm_bcr, bar, 0, rr, seq);
+      if constexpr (BCF32) {
+        tma_load_3d(&s.bc[0][0][0], &tm_bcf, bar, 0, rf, seq);
+        tma_load_3d(&s.bc[1][0][0], &tm_bcr, bar, 0, rr, seq);
+      } else {
+        tma_load_3d(&s.bc_raw[0][0][0], &tm_bcf, bar, 0, rf, seq);
+        tma_load_3d(&s.bc_raw[1][0][0], &tm_bcr, bar, 0, rr, seq);
+      }
       tma_load_3d(&s.d[0][0][0], &tm_df, bar, e0, rf, seq);
       tma_load_3d(&s.d[1][0][0], &tm_dr, bar, e0, rr, seq);
     }
@@ -334,7 +358,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   // FUSEDT, one thread: delta of chunk c (its dt tile has landed in `stage`) -> TMEM columns [32 stage, 32 stage + 32)
   auto issue_dt_mma = [&](int c, int stage) {
     if constexpr (FUSEDT) {
-      mbar_wait(&dt_bar[stage], (c >> 1) & 1);
+      mbar_wait_or_trap(&dt_bar[stage], (c >> 1) & 1);
       tc_fence_after();
       constexpr uint32_t idesc = make_idesc_bf16(128, 2 * kScanTC);
       const uint64_t da = make_smem_desc_sw128(smem_u32(&sm.wdt[0][0][0]));
@@ -362,11 +386,12 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     }
     issue(0, 0);
     if constexpr (FUSEDT) {
-      mbar_wait(&w_bar, 0);
+      mbar_wait_or_trap(&w_bar, 0);
       issue_dt_mma(0, 0);
     }
   }
-  if constexpr (FUSEDT) mbar_wait(&w_bar, 0);   // every later MMA issuer has observed the weight tile's arrival
+  if constexpr (FUSEDT) mbar_wait_or_trap(&w_bar, 0);   // every later MMA issuer has observed the weight tile's arrival
+  bool prev_mixed = false;
   for (int c = 0; c < nch; ++c) {
     const int stage = c & 1;
     // Issue work: TMA by warp 0, the dt_proj MMA by warp 2 (a different scheduler: every instruction of these paths is on the
@@ -383,39 +408,53 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     const int i0 = c * kScanTC;
     const int nsteps = min(kScanTC, Lrun - i0);
     const bool has_final = (L - 1 - (i0 + nsteps - 1)) < i0 + nsteps;
-    mbar_wait(&full_bar[stage], (c >> 1) & 1);
-    // B|C to fp32, once per chunk, 4 values per thread (B carries the ln 2 of the log2-domain delta on the fast
-    // path); the reverse direction's rows are un-flipped here so that the main loop indexes both alike
+    // (the fused kernel's barriers depend on descriptors and byte counts of two more async engines: a mistake there must
+    // trap, not hang the GPU)
+    if constexpr (MODE != kScanPlain) mbar_wait_or_trap(&full_bar[stage], (c >> 1) & 1);
+    else mbar_wait(&full_bar[stage], (c >> 1) & 1);
+    float (*ys)[kScanTC][kScanCH] = ys_all[BCF32 ? (c & 1) : 0];
+    const bool late_chunk = (L - 1 - i0) < i0;   // every position of the chunk was parked in an earlier chunk
+    const bool mixed_chunk = has_final && !late_chunk;   // the middle of the sequence: park, combine and finalise side by side
+    if constexpr (!BCF32) {
+      // B|C to fp32, once per chunk, 4 values per thread (B carries the ln 2 of the log2-domain delta on the fast
+      // path); the reverse direction's rows are un-flipped here so that the main loop indexes both alike
 #pragma unroll
-    for (int gi = tid; gi < 2 * kScanTC * 2 * kScanN / 4; gi += kScanThreads) {   // 256 groups of 4 values
-      const int dd = gi >> 7, r = gi & 127;
-      const int j = r >> 3, k0 = (r & 7) * 4;
-      const T* src;
-      if constexpr (FUSEDT) src = &sm.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
-      else src = &s.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
-      float4 v;
-      if constexpr (sizeof(T) == 2) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(src);
-        v.x = __uint_as_float(raw.x << 16); v.y = __uint_as_float(raw.x & 0xffff0000u);
-        v.z = __uint_as_float(raw.y << 16); v.w = __uint_as_float(raw.y & 0xffff0000u);
-      } else {
-        v = *reinterpret_cast<const float4*>(src);
+      for (int gi = tid; gi < 2 * kScanTC * 2 * kScanN / 4; gi += kScanThreads) {   // 256 groups of 4 values
+        const int dd = gi >> 7, r = gi & 127;
+        const int j = r >> 3, k0 = (r & 7) * 4;
+        const T* src;
+        if constexpr (FUSEDT) src = &sm.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
+        else src = &s.bc_raw[dd][dd ? kScanTC - 1 - j : j][k0];
+        float4 v;
+        if constexpr (sizeof(T) == 2) {
+          const uint2 raw = *reinterpret_cast<const uint2*>(src);
+          v.x = __uint_as_float(raw.x << 16); v.y = __uint_as_float(raw.x & 0xffff0000u);
+          v.z = __uint_as_float(raw.y << 16); v.w = __uint_as_float(raw.y & 0xffff0000u);
+        } else {
+          v = *reinterpret_cast<const float4*>(src);
+        }
+        if (k0 < kScanN) { v.x *= bscale; v.y *= bscale; v.z *= bscale; v.w *= bscale; }
+        *reinterpret_cast<float4*>(&sm.bc[dd][j][k0]) = v;
       }
-      if (k0 < kScanN) { v.x *= bscale; v.y *= bscale; v.z *= bscale; v.w *= bscale; }
-      *reinterpret_cast<float4*>(&sm.bc[dd][j][k0]) = v;
-    }
-    __syncthreads();   // sm.bc is complete; chunk c-1's epilogue (its parked partials, its reads of ys / pz) is done
-    if constexpr (FUSEDT) {
-      // the single B|C landing buffer has been consumed: only now may the next chunk's loads go out (they still have this
-      // chunk's whole main loop to arrive)
-      if (tma_warp && c + 1 < nch) {
-        if (elect_one()) issue(c + 1, stage ^ 1);
+      __syncthreads();   // sm.bc is complete; chunk c-1's epilogue (its parked partials, its reads of ys / pz) is done
+      if constexpr (FUSEDT) {
+        // the single B|C landing buffer has been consumed: only now may the next chunk's loads go out (they still have this
+        // chunk's whole main loop to arrive)
+        if (tma_warp && c + 1 < nch) {
+          if (elect_one()) issue(c + 1, stage ^ 1);
+        }
       }
+    } else {
+      // No conversion pass and no barrier here: the stage holds fp32 rows, ys is double-buffered, and in the block-uniform
+      // ("late") path every thread prefetches into the very pz items it reads back in the epilogue.  Only the generic path of
+      // the middle chunk indexes pz across threads: it (and the chunk after it) orders its prefetch behind the previous
+      // epilogue with a barrier of its own.
+      if (mixed_chunk || prev_mixed) __syncthreads();
+      prev_mixed = mixed_chunk;
     }
     // Positions of this chunk that the other direction visited in an EARLIER chunk will be finalised in the
     // epilogue: fetch their parked partials and z rows now (every earlier epilogue is complete and visible after the
     // barrier above), so that the epilogue does not wait on global memory.
-    const bool late_chunk = (L - 1 - i0) < i0;   // every position of the chunk was parked in an earlier chunk
     if (sizeof(T) == 2 && late_chunk) {
       // block-uniform fast path (bf16): one (step, segment) item per thread and direction, no per-item classification
       const int j = tid / kScanSeg8, seg = tid % kScanSeg8;
@@ -444,8 +483,12 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     cp_async_commit();
 
     if constexpr (FUSEDT) tc_fence_after();   // delta of the chunk is in TMEM (the wait on full_bar above covered the MMA)
-    if (active) {
-      const float* bcp = &sm.bc[dir][0][0];
+    // FUSEDT: tcgen05.ld is .sync.aligned -- every lane of a warp must execute it, so lanes (and whole warps) past E run the
+    // recurrence too, on the zeros the TMA filled in for them (E is a multiple of 64 in every model; this is for the op API)
+    if (active || FUSEDT) {
+      const float* bcp;
+      if constexpr (BCF32) bcp = &s.bc[dir][0][0];
+      else bcp = &sm.bc[dir][0][0];
       float* ysp = &ys[dir][0][ch];
       auto run_chunk = [&](auto rev_tag) {
         constexpr bool REV = decltype(rev_tag)::value != 0;   // compile-time row order: immediate offsets in the unrolled loop
@@ -459,7 +502,8 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
         auto advance = [&](int j, int jn, float draw_n) -> float {
           const float uu_n = ActT<T>::to_f(up[row(jn)]);
           const float dl_n = S.delta(draw_n);
-          const float yv = S.step(dl, dl * uu, Dskip * uu, bcp + j * 2 * kScanN);
+          // (fp32 rows straight from the TMA box are in box order: the reverse direction's step j is row 15 - j)
+          const float yv = S.step(dl, dl * uu, Dskip * uu, bcp + (BCF32 && REV ? kScanTC - 1 - j : j) * 2 * kScanN);
           uu = uu_n;
           dl = dl_n;
           return yv;
@@ -639,19 +683,43 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
   }
 }
 
+// B|C columns of the two x_proj outputs ([rows, ldbc] bf16, B at bc_off, C at bc_off + 16) -> float [2][rows][32] rows
+// [B ln 2 | C]: what the kScanBcF32 kernel's TMA delivers (the ln 2 is owed by the log2-domain delta, see ScanDir<false>).
+// One thread per 8 values.  128 bytes per token and direction written once and read once: < 2 % of the scan's traffic.
+__global__ void bc_to_f32_kernel(const bf16* __restrict__ dbc_f, const bf16* __restrict__ dbc_r, long long ldbc, int bc_off,
+                                 float* __restrict__ out, long long rows) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= rows * 8) return;
+  const int q = static_cast<int>(idx & 3), dd = static_cast<int>((idx >> 2) & 1);
+  const long long r = idx >> 3;
+  const uint4 raw = *reinterpret_cast<const uint4*>((dd ? dbc_r : dbc_f) + r * ldbc + bc_off + 8 * q);
+  const float sc = q < 2 ? kLn2 : 1.0f;
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  float4 o0, o1;
+  o0.x = __uint_as_float(w[0] << 16) * sc; o0.y = __uint_as_float(w[0] & 0xffff0000u) * sc;
+  o0.z = __uint_as_float(w[1] << 16) * sc; o0.w = __uint_as_float(w[1] & 0xffff0000u) * sc;
+  o1.x = __uint_as_float(w[2] << 16) * sc; o1.y = __uint_as_float(w[2] & 0xffff0000u) * sc;
+  o1.z = __uint_as_float(w[3] << 16) * sc; o1.w = __uint_as_float(w[3] & 0xffff0000u) * sc;
+  float4* op = reinterpret_cast<float4*>(out + (static_cast<long long>(dd) * rows + r) * 2 * kScanN + 8 * q);
+  op[0] = o0;
+  op[1] = o1;
+}
+
 // FUSEDT = true: delta_f / delta_r are the x_proj outputs ([S*L, ldbc], dt in columns 0..R-1, ldbc >= 64) and wdt_f / wdt_r
 // the dt_proj weights [E, R] (row pitch ldw, a multiple of 8 elements; R <= 64); otherwise delta_* are [S*L, E] and wdt_* unused.
-template <typename T, bool PRECISE, bool FUSEDT = false>
+template <typename T, bool PRECISE, int MODE = kScanPlain>
 inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, const T* u_r, const T* delta_r,
                                  const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
                                  const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
                                  const float* D_r, const float* bias_r, T* y, int S, int L, int E,
                                  cudaStream_t stream, const T* wdt_f = nullptr, const T* wdt_r = nullptr, long long ldw = 0,
-                                 int R = 0, const float* h0 = nullptr, int Lrun = 0) {
-  size_t smem = sizeof(ScanShared<T, FUSEDT>);
+                                 int R = 0, const float* h0 = nullptr, int Lrun = 0, const float* bcf_f = nullptr,
+                                 const float* bcf_r = nullptr) {
+  constexpr bool FUSEDT = MODE == kScanFusedDt, BCF32 = MODE == kScanBcF32;
+  size_t smem = sizeof(ScanShared<T, MODE>);
   if (const char* ex = getenv("PCAD_SCAN_EXTRA_SMEM")) smem += static_cast<size_t>(atoi(ex));   // occupancy experiments
   static unsigned long long attr_done = 0;
-  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, FUSEDT>, static_cast<int>(smem), attr_done);
+  cudaError_t e1 = ensure_dynamic_smem(biscan_kernel<T, PRECISE, MODE>, static_cast<int>(smem), attr_done);
   if (e1 != cudaSuccess) return e1;
   constexpr bool f32 = sizeof(T) == 4;
   CUtensorMap tm[8];
@@ -668,11 +736,17 @@ inline cudaError_t launch_biscan(const T* u_f, const T* delta_f, const T* bc_f, 
     tm[6] = tm[0];
     tm[7] = tm[0];
   }
-  ok = ok && make_tmap_3d(&tm[4], f32, bc_f + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
-  ok = ok && make_tmap_3d(&tm[5], f32, bc_r + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
+  if (BCF32) {   // bcf_*: float [S*L, 32] rows [B ln 2 | C] (bc_to_f32_kernel)
+    if (!bcf_f || !bcf_r) return cudaErrorInvalidValue;
+    ok = ok && make_tmap_3d(&tm[4], true, bcf_f, 2 * kScanN, L, S, 2 * kScanN, 2 * kScanN, kScanTC);
+    ok = ok && make_tmap_3d(&tm[5], true, bcf_r, 2 * kScanN, L, S, 2 * kScanN, 2 * kScanN, kScanTC);
+  } else {
+    ok = ok && make_tmap_3d(&tm[4], f32, bc_f + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
+    ok = ok && make_tmap_3d(&tm[5], f32, bc_r + bc_off, 2 * kScanN, L, S, ldbc, 2 * kScanN, kScanTC);
+  }
   if (!ok) return cudaErrorInvalidValue;
   dim3 grid((E + kScanCH - 1) / kScanCH, S);
-  biscan_kernel<T, PRECISE, FUSEDT><<<grid, kScanThreads, smem, stream>>>(
+  biscan_kernel<T, PRECISE, MODE><<<grid, kScanThreads, smem, stream>>>(
       tm[0], tm[1], tm[4], tm[2], tm[3], tm[5], tm[6], tm[7], (R + 15) / 16, z, ldz, A_f, D_f, bias_f, A_r, D_r, bias_r, y, L, E,
       h0, (Lrun > 0 && Lrun < L) ? Lrun : L);
   return cudaGetLastError();
@@ -783,7 +857,8 @@ inline cudaError_t launch_biscan_time_parallel(const T* u_f, const T* delta_f, c
                                                const T* bc_r, long long ldbc, int bc_off, const T* z, long long ldz,
                                                const float* A_f, const float* D_f, const float* bias_f, const float* A_r,
                                                const float* D_r, const float* bias_r, T* y, int S, int L, int E, int P,
-                                               float* state, float* sumd, cudaStream_t stream) {
+                                               float* state, float* sumd, cudaStream_t stream, const float* bcf_f = nullptr,
+                                               const float* bcf_r = nullptr) {
   if (P < 2 || L % P) return cudaErrorInvalidValue;
   const int Lseg = L / P;
   dim3 grid((E + kScanCH - 1) / kScanCH, S * P);
@@ -793,8 +868,13 @@ inline cudaError_t launch_biscan_time_parallel(const T* u_f, const T* delta_f, c
   scan_segment_carry_kernel<PRECISE><<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(A_f, A_r, state, sumd, S, P, E);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  return launch_biscan<T, PRECISE, false>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, bias_f, A_r, D_r,
-                                          bias_r, y, S * P, Lseg, E, stream, nullptr, nullptr, 0, 0, state);
+  if constexpr (sizeof(T) == 2 && !PRECISE) {
+    if (bcf_f && bcf_r)
+      return launch_biscan<T, PRECISE, kScanBcF32>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, bias_f, A_r,
+                                                   D_r, bias_r, y, S * P, Lseg, E, stream, nullptr, nullptr, 0, 0, state, 0, bcf_f, bcf_r);
+  }
+  return launch_biscan<T, PRECISE, kScanPlain>(u_f, delta_f, bc_f, u_r, delta_r, bc_r, ldbc, bc_off, z, ldz, A_f, D_f, bias_f, A_r, D_r,
+                                               bias_r, y, S * P, Lseg, E, stream, nullptr, nullptr, 0, 0, state);
 }
 
 }  // namespace pcad

@@ -256,14 +256,6 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_major(int M, int N, int a
   return make_idesc_bf16(M, N) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16);
 }
 
-// mbarrier wait that traps instead of spinning forever if a phase never completes (a wrong descriptor or byte count would
-// otherwise hang the GPU; ~2^28 polls is seconds, far beyond any legitimate wait)
-__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 28); ++i)
-    if (mbar_try_wait(bar, parity)) return;
-  asm volatile("trap;");
-}
-
 struct SsdSmem {
   static constexpr int kX0 = 0, kX1 = kSsdTile, kB = 2 * kSsdTile, kC = 3 * kSsdTile, kM = 4 * kSsdTile;   // M: 2 tiles
   static constexpr int kS = 6 * kSsdTile;                  // one head's state, bf16 [64 p][64 n] (8 KB)
@@ -337,14 +329,16 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
   const int head_d = 2 * hp + dh;
   const float A_l2 = Ap[head_d] * kLog2e, bias_d = bp[head_d];
 
-  // raw dt of the chunk about to be processed, fetched one iteration ahead (its global-load latency is off the critical path)
-  auto load_dt = [&](int it_) -> float {
-    if (it_ >= nch) return 0.f;
+  // raw dt of the chunk about to be processed, fetched one iteration ahead and kept as RAW BITS until it is used (converting
+  // at the load would make the thread wait for the load there and then: its global-load latency must stay off the critical path)
+  constexpr uint32_t kDtPastEnd = 0xff80u;   // bf16 -inf: row past the end (dt = 0)
+  auto load_dt = [&](int it_) -> uint32_t {
+    if (it_ >= nch) return kDtPastEnd;
     const int c_ = dir ? nch - 1 - it_ : it_;
     const int pos = c_ * kSsdQ + dtp;
-    return pos < L ? __bfloat162float(dt_raw[(row0 + pos) * ld_dt + head_d]) : -1e30f;   // -1e30: row past the end (dt = 0)
+    return pos < L ? static_cast<uint32_t>(reinterpret_cast<const unsigned short*>(dt_raw)[(row0 + pos) * ld_dt + head_d]) : kDtPastEnd;
   };
-  float dt_next = load_dt(0);
+  uint32_t dt_next = load_dt(0);
   uint32_t tma_phase = 0, mma_phase = 0;
   constexpr uint32_t idesc_g1 = make_idesc_bf16_major(128, 128, 0, 0);
   constexpr uint32_t idesc_g2 = make_idesc_bf16_major(128, 64, 0, 1);
@@ -354,7 +348,7 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
   for (int it = 0; it < nch; ++it) {
     const int c = dir ? nch - 1 - it : it;
     const int p0 = c * kSsdQ;
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {   // whole warp, then elect.sync: issue instructions back to back
       mbar_arrive_expect_tx(tma_bar, 4 * kSsdTile);
       tma_load_3d(sm + SsdSmem::kX0, tm, tma_bar, (2 * hp) * kSsdP, p0, seq);
       tma_load_3d(sm + SsdSmem::kX1, tm, tma_bar, (2 * hp + 1) * kSsdP, p0, seq);
@@ -374,7 +368,7 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
     }
     // ---- dt, log-decay and its cumulative sum in scan order
     {
-      const float raw = dt_next;
+      const float raw = __uint_as_float(dt_next << 16);
       dt_next = load_dt(it + 1);
       const float dtv = raw > -1e29f ? softplus<true>(raw + bias_d) : 0.f;
       float v = dtv * A_l2;
@@ -424,7 +418,7 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
     // ---- GEMM1: G = C B^T
     mbar_wait_or_trap(tma_bar, tma_phase);
     tma_phase ^= 1;
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {   // whole warp, then elect.sync: issue instructions back to back
       tc_fence_after();
       const uint64_t da = make_smem_desc_sw128(sm_addr + SsdSmem::kC), db = make_smem_desc_sw128(sm_addr + SsdSmem::kB);
 #pragma unroll
@@ -531,7 +525,7 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
     };
     // GEMM2: Y = M X_h;  GEMM4: Y' = C S^T;  then every thread waits for both
     auto mma_head = [&](int h) {
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {   // whole warp, then elect.sync: issue instructions back to back
         tc_fence_after();
         const uint32_t xa = sm_addr + (h ? SsdSmem::kX1 : SsdSmem::kX0);
         const uint64_t db = make_smem_desc_mn_sw128(xa, 16);
@@ -614,7 +608,7 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
     }
     if (more) {
       // ---- GEMM3: S_c[(h, p), n] = sum_s Xw[s, (h, p)] B[s, n]
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {   // whole warp, then elect.sync: issue instructions back to back
         tc_fence_after();
         const uint64_t da = make_smem_desc_mn_sw128(sm_addr + SsdSmem::kM, kSsdTile);
         const uint64_t db = make_smem_desc_mn_sw128(sm_addr + SsdSmem::kB, 16);

@@ -161,6 +161,27 @@ def test_bf16_in_kernel_dt_proj_matches_separate_gemm(Model, cuda_device, monkey
     assert (a - b).abs().max().item() <= 1e-2
 
 
+@pytest.mark.parametrize("B,L,mask_at", [(3, 200, 100), (2, 37, 5), (1, 512, 255), (2, 16, 15), (1, 1024, 1000)])
+def test_scan_fp32_bc_rows_mode_is_bit_identical(Model, cuda_device, monkeypatch, B, L, mask_at):
+    """The forward converts B|C to fp32 rows once per layer (bc_to_f32_kernel) and runs the scan in its one-barrier mode
+    (scan.cuh kScanBcF32); PCAD_SCAN_BC_F32=0 keeps the in-kernel conversion.  Same arithmetic in the same order: the logits,
+    the hidden states and the score-only entry point (pruned last layer) must be bit-identical, ragged lengths included."""
+    cfg = CaduceusConfig(d_model=256, n_layer=3)
+    sd = random_init_state_dict(cfg, seed=7)
+    ids = make_ids(B, L, seed=3, mask_at=mask_at)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PCAD_SCAN_BC_F32", flag)
+        m = Model.from_pretrained(sd, config=cfg, torch_dtype=torch.bfloat16).to(cuda_device)
+        o = m(input_ids=ids.to(cuda_device), output_hidden_states=True)
+        sc = m.score_masked(ids.to(cuda_device), mask_at)
+        outs.append((o.logits.cpu(), o.hidden_states[-1].cpu(), sc.cpu(), m.launch_count()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert not torch.isnan(outs[0][0]).any()
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_engine_rc_equivariance(Model, cuda_device, dtype):
     """Size-independent property: logits(RC(ids)) == logits(ids).flip(L)[..., comp]."""
