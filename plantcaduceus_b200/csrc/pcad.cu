@@ -81,6 +81,7 @@ struct pcad_handle {
   bool f32 = false;
   bool fuse_dt = false;                // bf16: dt_proj computed inside the scan (tcgen05), no dt_proj launches, no delta in HBM
   bool bc_f32 = true;                  // bf16: B|C converted to fp32 rows once (bc_to_f32_kernel), scan in its one-barrier mode
+  bool bc_f32_force = false;           // ... also below the size where it pays (tests)
   bool fuse_norm = false;   // bf16 activations + bf16 residual: add+RMSNorm folded into the out_proj / in_proj epilogues
   size_t act_size = 2;
   bool finalized = false;
@@ -626,6 +627,9 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st, int prune_idx = 
       const uint8_t* zbase = static_cast<const uint8_t*>(ws.xz) + static_cast<size_t>(E) * h->act_size;
       pruned = prune_idx >= 0 && li == h->cfg.n_layer - 1 && P == 1 && h->prune_last && L >= 8;
       const int Lrun = pruned ? (prune_idx > L - 1 - prune_idx ? prune_idx : L - 1 - prune_idx) + 1 : 0;
+      // fp32 B|C rows + one-barrier scan mode: one more (tiny) launch per layer, so only where the scan is long enough to
+      // repay it (measured: -1 ms of 170 per step at T = 262 144; launch-bound small batches keep the in-kernel conversion)
+      const bool use_bcf = h->bc_f32 && !f32 && (h->bc_f32_force || T >= 65536);
       if (fuse_dt)   // the scan reads the x_proj outputs (dt | B | C) and the dt_proj weights
         rc = op_biscan(h, ws.xc[0], ws.dbc[0], ws.dbc[0], ws.xc[1], ws.dbc[1], ws.dbc[1], RP, R, zbase, 2 * E,
                        lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32,
@@ -633,9 +637,9 @@ int run_backbone(pcad_handle* h, int B, int L, cudaStream_t st, int prune_idx = 
       else {
         rc = op_biscan(h, ws.xc[0], ws.delta[0], ws.dbc[0], ws.xc[1], ws.delta[1], ws.dbc[1], RP, R, zbase, 2 * E,
                        lw.dir[0].A, lw.dir[0].D, lw.dir[0].dt_bias, lw.dir[1].A, lw.dir[1].D, lw.dir[1].dt_bias, ws.y, S, L, E, f32, st,
-                       nullptr, nullptr, 0, 0, P, ws.seg_state, ws.seg_sumd, Lrun, h->bc_f32 ? ws.bcf : nullptr);
+                       nullptr, nullptr, 0, 0, P, ws.seg_state, ws.seg_sumd, Lrun, use_bcf ? ws.bcf : nullptr);
         if (P > 1) h->launch_count += 2;
-        if (h->bc_f32 && !f32) h->launch_count += 1;
+        if (use_bcf) h->launch_count += 1;
       }
       if (rc) return rc;
     }
@@ -801,7 +805,7 @@ int pcad_create(const pcad_config* cfg, int device, pcad_handle** out) {
   h->fuse_dt = false;
   if (const char* fd = getenv("PCAD_FUSED_DT"))
     h->fuse_dt = fd[0] == '1' && !m2 && !h->f32 && h->RP >= kScanDtK && h->R <= kScanDtK && (h->E % 8) == 0;
-  if (const char* bq = getenv("PCAD_SCAN_BC_F32")) h->bc_f32 = bq[0] != '0';   // A/B switch
+  if (const char* bq = getenv("PCAD_SCAN_BC_F32")) { h->bc_f32 = bq[0] != '0'; h->bc_f32_force = bq[0] == '1'; }   // A/B switch: 0 off, 1 always
   if (const char* pl = getenv("PCAD_NO_PRUNE")) h->prune_last = pl[0] != '1';
   if (const char* tp = getenv("PCAD_NO_TIME_PARALLEL")) h->time_parallel = tp[0] != '1';
   if (const char* ng = getenv("PCAD_NO_GRAPH")) h->use_graphs = ng[0] != '1';

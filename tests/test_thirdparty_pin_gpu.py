@@ -134,71 +134,12 @@ def test_biscan_matches_mamba_ssm_kernel_port(cuda_device, S, L, E, R):
     assert (y - want).abs().max().item() <= 1e-4 * scale + 1e-5
 
 
-# ---- depthwise causal conv + SiLU against vLLM's causal_conv1d_fn (library code, checker only) -------------------------
-# vLLM's causal_conv1d_fn is its re-implementation (Triton, continuous-batching calling convention) of causal-conv1d's
-# causal_conv1d_fn -- the call Mamba.forward makes [EXT causal_conv1d_fn(x, conv1d.weight, conv1d.bias, activation="silu")].
-# Not the reference's own CUDA kernel, but an independent implementation of the same interface by a third party; the conv is
-# also pinned, together with the whole mixer, by transformers' MambaMixer / Mamba2Mixer in tests/test_oracle.py.
-@pytest.mark.parametrize("S,L,E", [(3, 512, 768), (2, 70, 256), (1, 5, 128)])
-def test_conv_silu_matches_vllm_causal_conv1d(cuda_device, S, L, E):
-    """pcad_op_conv_silu (fp32; forward direction, and the reverse direction = the same conv on the time-flipped sequence,
-    flipped back) == vLLM's causal_conv1d_fn with zero initial state, and the oracle's F.conv1d formulation == both."""
-    try:
-        from vllm.model_executor.layers.mamba.ops.causal_conv1d import causal_conv1d_fn
-    except Exception as e:  # pragma: no cover
-        pytest.skip(f"vLLM causal_conv1d_fn not importable: {type(e).__name__}: {e}")
-    from plantcaduceus_b200 import _lib
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(S * 1000 + L)
-    xz = torch.randn(S * L, 2 * E, generator=g).to(cuda_device)          # conv reads the x half, pitch 2E
-    w = [torch.randn(E, 4, generator=g).to(cuda_device) for _ in range(2)]
-    b = [torch.randn(E, generator=g).to(cuda_device) for _ in range(2)]
-    out = [torch.empty(S * L, E, device=cuda_device) for _ in range(2)]
-    ptr = lambda t: C.c_void_p(t.data_ptr())
-    rc = lib.pcad_op_conv_silu(ptr(xz), 2 * E, ptr(w[0]), ptr(b[0]), ptr(w[1]), ptr(b[1]), ptr(out[0]), ptr(out[1]), S, L, E, F32,
-                               C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    assert rc == 0, lib.pcad_last_error(None)
-    torch.cuda.synchronize()
-    x = xz[:, :E].contiguous()                                            # [S*L, E] token-major = channel-last
-    qsl = torch.arange(0, (S + 1) * L, L, device=cuda_device, dtype=torch.int32)
-    for k in range(2):
-        xin = x if k == 0 else x.reshape(S, L, E).flip(1).reshape(S * L, E).contiguous()
-        ref = F.silu(F.conv1d(xin.cpu().reshape(S, L, E).transpose(1, 2), w[k].cpu()[:, None, :], b[k].cpu(), padding=3,
-                              groups=E)[..., :L]).transpose(1, 2)
-        if k == 1:
-            ref = ref.flip(1)
-        ref = ref.reshape(S * L, E)
-        scale = ref.abs().max().item()
-        tol = 1e-5 * scale + 1e-6
-        assert (out[k].cpu() - ref).abs().max().item() <= tol, f"direction {k}: engine vs F.conv1d"
-
-        def vllm_conv():
-            # The launcher's program table (which sequence / which 8-token block a Triton program handles) is handed in the way
-            # vLLM's own metadata builder does: without it the function fills a table inside the grid callback, which does not
-            # reliably reach the launch when called standalone (outputs left unwritten).
-            from types import SimpleNamespace
-            nb = (L + 7) // 8
-            bp = torch.arange(S, dtype=torch.int32).repeat_interleave(nb).to(cuda_device)
-            tp = torch.arange(nb, dtype=torch.int32).repeat(S).to(cuda_device)
-            entry = dict(tot=S * nb, mlist=bp, mlist_len=S * nb, offsetlist=tp, batch_ptr=bp, token_chunk_offset_ptr=tp)
-            meta = SimpleNamespace(nums_dict={8: entry}, batch_ptr=bp, token_chunk_offset_ptr=tp)
-            states = torch.zeros(S, 3, E, device=cuda_device).transpose(1, 2)   # (batch, dim, width - 1), channel-last
-            r = causal_conv1d_fn(xin.t(), w[k], b[k], states, qsl,
-                                 cache_indices=torch.arange(S, device=cuda_device, dtype=torch.int32),
-                                 has_initial_state=torch.zeros(S, device=cuda_device, dtype=torch.bool), activation="silu",
-                                 metadata=meta)
-            torch.cuda.synchronize()
-            r = r.t().reshape(S, L, E)
-            return (r.flip(1) if k == 1 else r).reshape(S * L, E)
-        try:
-            want = vllm_conv()
-        except Exception as e:
-            pytest.skip(f"causal_conv1d_fn refused the call: {type(e).__name__}: {e}")
-        assert (want.cpu() - ref).abs().max().item() <= tol, f"direction {k}: vLLM causal_conv1d_fn vs F.conv1d"
-        assert (out[k] - want).abs().max().item() <= tol, f"direction {k}: engine vs vLLM causal_conv1d_fn"
-
-
 # ---- fused add + RMSNorm against vLLM's CUDA kernel (library code, checker only) ---------------------------------------
+# (The conv is NOT pinned to vLLM: its causal_conv1d_fn is a Triton re-implementation with a continuous-batching calling
+# convention, not a port of the causal-conv1d CUDA kernel, and called standalone on the GPU box -- with or without a
+# hand-built program table -- it leaves most of its output unwritten (zeros / NaN; tried in rounds 2a and 2b, three
+# call forms).  The conv is pinned instead, together with the whole mixer, by transformers' MambaMixer / Mamba2Mixer in
+# tests/test_oracle.py, and the engine's kernel by F.conv1d in tests/test_ops_gpu.py::test_conv_silu_both_directions.)
 @pytest.mark.parametrize("rows,d", [(300, 384), (64, 1024)])
 def test_add_rmsnorm_matches_vllm_fused_add_rms_norm(cuda_device, rows, d):
     """pcad_op_add_rmsnorm (fp32) == torch.ops._C.fused_add_rms_norm (in place: residual <- x + residual,
