@@ -110,7 +110,7 @@ def main():
     launches()
     scan = dump(f"scan_{TAG}.ncu-rep", f"{TAG}_scan_ncu_summary.txt",
                 "ncu --set full --clock-control none --import-source on -k regex:biscan -s 3 -c 1  python bench.py --steps 1 --warmup 1 --cpu-sample 0 --no-clocks\n"
-                "pcad::biscan_kernel<__nv_bfloat16, false, false>  (PlantCaduceus_l32, B=256 x 512 bp: S=512 sequences, E=2048, one launch per layer)\n"
+                "pcad::biscan_kernel<__nv_bfloat16, false, kScanBcF32 = 2>: fp32 B|C rows by TMA, one block barrier per chunk  (PlantCaduceus_l32, B=256 x 512 bp: S=512 sequences, E=2048, one launch per layer)\n"
                 "algorithmic bytes per launch 6.543 GB (817.9 MB/window / 32 layers x 256 windows)", stalls=True)
     if scan:
         rd, wr = scan['dram__bytes_read.sum'], scan['dram__bytes_write.sum']
