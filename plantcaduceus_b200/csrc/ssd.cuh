@@ -103,6 +103,17 @@ __device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
   }
 }
 
+// one 32-bit word of two bf16 <-> a packed fp32 pair (FMUL2 / FFMA2 operate on the pair in one issue slot)
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) {
+  return pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f32x2_to_bf16x2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) { return pack2(__uint_as_float(lo), __uint_as_float(hi)); }
+
 // ---------------------------------------------------------------------------------------------------------------------
 // gated RMSNorm of both directions + add
 // ---------------------------------------------------------------------------------------------------------------------
@@ -449,6 +460,7 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
       for (int w = 0; w < 4; ++w)
         if (dir == 0 ? (w < I) : (w > I)) rI += wsum[h * 4 + w];
       const float rowf = ex2_approx(cum_t - rI);
+      const f32x2 rowf2 = pack2(rowf, rowf), cumt2 = pack2(cum_t, cum_t), neg1 = pack2(-1.0f, -1.0f);
       const float* cf = colf + (h * 4 + I) * 128;
       auto kind = [&](int kk) {   // 0 masked, 1 diagonal, 2 full
         const int J = (2 * kk + half) >> 1;
@@ -472,17 +484,15 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
             *reinterpret_cast<uint4*>(mrow + (((c0 + g) ^ (trow & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
         } else if (kd == 2) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int g = 0; g < 2; ++g) {   // (G rowf) colf on packed pairs: two multiplies per PAIR of elements
             const float4 f0 = *reinterpret_cast<const float4*>(&cf[s0 + 8 * g]);
             const float4 f1 = *reinterpret_cast<const float4*>(&cf[s0 + 8 * g + 4]);
-            const float ff[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-            float v[8];
+            const f32x2 ff[4] = {pack2(f0.x, f0.y), pack2(f0.z, f0.w), pack2(f1.x, f1.y), pack2(f1.z, f1.w)};
+            uint32_t ow[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[kk & 1][8 * g + e]) * rowf * ff[e];
-            uint4 o;
-            o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-            o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(mrow + (((c0 + g) ^ (trow & 7)) << 4)) = o;
+            for (int q = 0; q < 4; ++q)
+              ow[q] = f32x2_to_bf16x2(mul2(mul2(pack2u(r[kk & 1][8 * g + 2 * q], r[kk & 1][8 * g + 2 * q + 1]), rowf2), ff[q]));
+            *reinterpret_cast<uint4*>(mrow + (((c0 + g) ^ (trow & 7)) << 4)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }
         } else {
 #pragma unroll
@@ -492,13 +502,17 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
             for (int q = 0; q < 2; ++q) {
               const float4 cs = *reinterpret_cast<const float4*>(&cums[h * 128 + s0 + 8 * g + 4 * q]);
               const float4 ds = *reinterpret_cast<const float4*>(&dts[h * 128 + s0 + 8 * g + 4 * q]);
-              const float cc[4] = {cs.x, cs.y, cs.z, cs.w}, dd[4] = {ds.x, ds.y, ds.z, ds.w};
+              const f32x2 cc2[2] = {pack2(cs.x, cs.y), pack2(cs.z, cs.w)}, dd2[2] = {pack2(ds.x, ds.y), pack2(ds.z, ds.w)};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int s = s0 + 8 * g + 4 * q + e;
-                const bool keep = dir == 0 ? (s <= trow) : (s >= trow);
-                const float val = __uint_as_float(r[kk & 1][8 * g + 4 * q + e]) * ex2_approx(cum_t - cc[e]) * dd[e];
-                v[4 * q + e] = keep ? val : 0.f;
+              for (int e2 = 0; e2 < 2; ++e2) {   // pairs: cum_t - cum_s, the two exponentials, G e dt
+                float x0, x1, v0, v1;
+                unpack2(fma2(cc2[e2], neg1, cumt2), x0, x1);
+                const f32x2 ee = pack2(ex2_approx(x0), ex2_approx(x1));
+                const int ri = 8 * g + 4 * q + 2 * e2;
+                unpack2(mul2(mul2(pack2u(r[kk & 1][ri], r[kk & 1][ri + 1]), ee), dd2[e2]), v0, v1);
+                const int s = s0 + ri;
+                v[4 * q + 2 * e2] = (dir == 0 ? (s <= trow) : (s >= trow)) ? v0 : 0.f;
+                v[4 * q + 2 * e2 + 1] = (dir == 0 ? (s + 1 <= trow) : (s + 1 >= trow)) ? v1 : 0.f;
               }
             }
             uint4 o;
@@ -550,6 +564,7 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
       const float cum_t = cums[h * 128 + trow];
       const float sc = it > 0 ? ex2_approx(cum_t) : 0.f;
       const float Dh = Dp[2 * hp + h];
+      const f32x2 sc2 = pack2(sc, sc), Dh2 = pack2(Dh, Dh);
       const uint8_t* xrow = sm + (h ? SsdSmem::kX1 : SsdSmem::kX0) + trow * 128;
       const int pos = p0 + trow;
       bf16* yp = yout + (row0 + pos) * E + (2 * hp + h) * kSsdP + 32 * half;
@@ -560,17 +575,17 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
         if (it > 0) tmem_ld_32x32b_x16(t_lane + 192 + 32 * half + 16 * k, yo);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float xv[8];
-          unpack8(*reinterpret_cast<const uint4*>(xrow + (((4 * half + 2 * k + g) ^ (trow & 7)) << 4)), xv);
-          float o[8];
+        for (int g = 0; g < 2; ++g) {   // packed pairs: y = Y + sc Y' + D x
+          const uint4 xr = *reinterpret_cast<const uint4*>(xrow + (((4 * half + 2 * k + g) ^ (trow & 7)) << 4));
+          const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+          uint32_t ow[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float v = __uint_as_float(yi[8 * g + e]);
-            if (it > 0) v = fmaf(sc, __uint_as_float(yo[8 * g + e]), v);
-            o[e] = fmaf(Dh, xv[e], v);
+          for (int q = 0; q < 4; ++q) {
+            f32x2 v = pack2u(yi[8 * g + 2 * q], yi[8 * g + 2 * q + 1]);
+            if (it > 0) v = fma2(sc2, pack2u(yo[8 * g + 2 * q], yo[8 * g + 2 * q + 1]), v);
+            ow[q] = f32x2_to_bf16x2(fma2(Dh2, bf16x2_to_f32x2(xw[q]), v));
           }
-          if (pos < L) store16<bf16>(yp + 16 * k + 8 * g, o);
+          if (pos < L) *reinterpret_cast<uint4*>(yp + 16 * k + 8 * g) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
       }
     };
@@ -578,17 +593,24 @@ ssd_chunk_tc_kernel(const __grid_constant__ CUtensorMap tm_f, const __grid_const
 
     // X w for both heads (into the M tiles), w_s = exp(cum_end - cum_s) dt_s
     auto build_Xw = [&]() {
-      for (int idx = tid; idx < 2 * kSsdQ * 8; idx += kSsdThreads) {
-        const int hh = idx >> 10, r = (idx >> 3) & 127, cp = idx & 7;
-        const float w = ex2_approx(wsum[8 + hh] - cums[hh * 128 + r]) * dts[hh * 128 + r];
-        float v[8];
-        unpack8(*reinterpret_cast<const uint4*>(sm + (hh ? SsdSmem::kX1 : SsdSmem::kX0) + r * 128 + cp * 16), v);
+      // thread = (head, position): its row of the x tile scaled by w into the same (swizzled) place of the M tile.  The eight
+      // 16-byte chunks are walked in the order chunk ^ (row & 7), so that eight consecutive rows touch eight different chunks:
+      // conflict-free quarter-warps on the 128-byte-pitch tiles.
+      const int hh = tid >> 7, r = tid & 127;
+      const float w = ex2_approx(wsum[8 + hh] - cums[hh * 128 + r]) * dts[hh * 128 + r];
+      const f32x2 w2 = pack2(w, w);
+      const uint8_t* src = sm + (hh ? SsdSmem::kX1 : SsdSmem::kX0) + r * 128;
+      uint8_t* dst = sm + SsdSmem::kM + hh * kSsdTile + r * 128;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= w;
+      for (int cp = 0; cp < 8; ++cp) {
+        const int pc = (cp ^ (r & 7)) << 4;
+        const uint4 raw = *reinterpret_cast<const uint4*>(src + pc);
         uint4 o;
-        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-        o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(sm + SsdSmem::kM + hh * kSsdTile + r * 128 + cp * 16) = o;
+        o.x = f32x2_to_bf16x2(mul2(bf16x2_to_f32x2(raw.x), w2));
+        o.y = f32x2_to_bf16x2(mul2(bf16x2_to_f32x2(raw.y), w2));
+        o.z = f32x2_to_bf16x2(mul2(bf16x2_to_f32x2(raw.z), w2));
+        o.w = f32x2_to_bf16x2(mul2(bf16x2_to_f32x2(raw.w), w2));
+        *reinterpret_cast<uint4*>(dst + pc) = o;
       }
     };
     // one copy of every piece (runtime phase index): phase 0 [M_0 S_0] MMA_0, phase 1 [y_0 M_1 S_1] MMA_1, phase 2 [y_1 Xw]
