@@ -391,7 +391,7 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     }
   }
   if constexpr (FUSEDT) mbar_wait_or_trap(&w_bar, 0);   // every later MMA issuer has observed the weight tile's arrival
-  bool prev_mixed = false;
+  bool prev_late = false;
   for (int c = 0; c < nch; ++c) {
     const int stage = c & 1;
     // Issue work: TMA by warp 0, the dt_proj MMA by warp 2 (a different scheduler: every instruction of these paths is on the
@@ -414,7 +414,6 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
     else mbar_wait(&full_bar[stage], (c >> 1) & 1);
     float (*ys)[kScanTC][kScanCH] = ys_all[BCF32 ? (c & 1) : 0];
     const bool late_chunk = (L - 1 - i0) < i0;   // every position of the chunk was parked in an earlier chunk
-    const bool mixed_chunk = has_final && !late_chunk;   // the middle of the sequence: park, combine and finalise side by side
     if constexpr (!BCF32) {
       // B|C to fp32, once per chunk, 4 values per thread (B carries the ln 2 of the log2-domain delta on the fast
       // path); the reverse direction's rows are un-flipped here so that the main loop indexes both alike
@@ -445,12 +444,16 @@ biscan_kernel(const __grid_constant__ CUtensorMap tm_uf, const __grid_constant__
         }
       }
     } else {
-      // No conversion pass and no barrier here: the stage holds fp32 rows, ys is double-buffered, and in the block-uniform
-      // ("late") path every thread prefetches into the very pz items it reads back in the epilogue.  Only the generic path of
-      // the middle chunk indexes pz across threads: it (and the chunk after it) orders its prefetch behind the previous
-      // epilogue with a barrier of its own.
-      if (mixed_chunk || prev_mixed) __syncthreads();
-      prev_mixed = mixed_chunk;
+      // No conversion pass, and normally no barrier here: the stage holds fp32 rows, ys is double-buffered, and in the
+      // block-uniform ("late") path every thread prefetches into the very pz items it reads back in the epilogue.  The one
+      // thing the old barrier still has to do happens in the middle of the sequence: a chunk that finalises positions must
+      // not fetch partials that the PREVIOUS chunk's epilogue (other threads, possibly still running) parked.  Once the
+      // previous chunk is itself "late", everything this chunk needs was parked at least two chunks -- two block barriers --
+      // ago (chunk c-1 late means L-1 < 32 (c-1), and the youngest partial chunk c reads comes from chunk (L-1-16c)/16 <= c-2);
+      // so only the first finalising chunk(s) pay: the middle chunk and the first late one.  The same barrier orders the
+      // middle chunk's cross-thread use of pz against its neighbours.
+      if (has_final && !prev_late) __syncthreads();
+      prev_late = late_chunk;
     }
     // Positions of this chunk that the other direction visited in an EARLIER chunk will be finalised in the
     // epilogue: fetch their parked partials and z rows now (every earlier epilogue is complete and visible after the

@@ -161,7 +161,8 @@ def test_bf16_in_kernel_dt_proj_matches_separate_gemm(Model, cuda_device, monkey
     assert (a - b).abs().max().item() <= 1e-2
 
 
-@pytest.mark.parametrize("B,L,mask_at", [(3, 200, 100), (2, 37, 5), (1, 512, 255), (2, 16, 15), (1, 1024, 1000)])
+@pytest.mark.parametrize("B,L,mask_at", [(3, 200, 100), (2, 37, 5), (1, 512, 255), (2, 16, 15), (1, 1024, 1000), (96, 512, 255),
+                                         (40, 528, 100)])
 def test_scan_fp32_bc_rows_mode_is_bit_identical(Model, cuda_device, monkeypatch, B, L, mask_at):
     """The forward converts B|C to fp32 rows once per layer (bc_to_f32_kernel) and runs the scan in its one-barrier mode
     (scan.cuh kScanBcF32); PCAD_SCAN_BC_F32=0 keeps the in-kernel conversion.  Same arithmetic in the same order: the logits,
