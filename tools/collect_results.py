@@ -54,6 +54,15 @@ def main():
             continue
         shutil.copy(os.path.join(OUT, f"r02_scale_n{n}.json"), os.path.join(PROF, f"r02_scale_n{n}.json"))
         lines.append(f"| {n} | {d['value']:.1f} | {d['ms_per_step']:.2f} | {(d.get('clocks') or {}).get('sm_mhz')} | profiles/r02_scale_n{n}.json |")
+    # the round's final code (one-barrier scan mode), one 8-GPU box, N = 8 then N = 1 back to back
+    f1, f8 = load("r02_final_scale_n1.json"), load("r02_final_scale_n8.json")
+    if f1 and f8:
+        lines += ["", "Final code of the round (scan in its one-barrier mode), one 8-GPU box, N = 8 then N = 1 back to back:", "",
+                  "| GPUs | variants/s | ms/step | e2e variants/s | x of 1 GPU | efficiency | SM MHz (rank 0) | file |", "|---|---|---|---|---|---|---|---|"]
+        for n, d in ((1, f1), (8, f8)):
+            shutil.copy(os.path.join(OUT, f"r02_final_scale_n{n}.json"), os.path.join(PROF, f"r02_final_scale_n{n}.json"))
+            x = d["value"] / f1["value"]
+            lines.append(f"| {n} | {d['value']:.1f} | {d['ms_per_step']:.2f} | {d['e2e']['value']:.1f} | {x:.2f} | {x / n:.3f} | {(d.get('clocks') or {}).get('sm_mhz')} | profiles/r02_final_scale_n{n}.json |")
     lines += ["", "`python bench.py --steps 20 --warmup 3` (N = 1) / `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps 20 --warmup 3`;",
               "the scores of all steps are gathered once after the last step, inside the timed region.  There is no data-path collective, and",
               "the reported time is the MAX over ranks: the step goes 284.7 ms (1 GPU) -> 290.9 ms (8 GPUs) because the slowest of eight",
