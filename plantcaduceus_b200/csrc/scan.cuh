@@ -13,8 +13,9 @@
 // one block overlap the main loops of the others, and a barrier waits for 4 warps, not 8); 124 registers let the
 // compiler keep a whole 8-step block in flight.  16 warps/SM are enough: the step is MUFU-bound, not latency-bound.
 // Step i advances the forward scan at t_f = i and the reverse scan at t_r = L-1-i.  Inputs are streamed in chunks
-// of 16 steps by TMA (3-D tensor maps, one issuing thread, 2-stage mbarrier ring: see biscan_kernel); the 32 B/C
-// values per step are converted to fp32 once per chunk and broadcast-read.  Each thread leaves its un-gated y for
+// of 16 steps by TMA (3-D tensor maps, one elected lane, 2-stage mbarrier ring: see biscan_kernel); the 32 B/C
+// values per step arrive as fp32 rows (kScanBcF32: converted once per layer by bc_to_f32_kernel) or are converted to fp32
+// once per chunk (kScanPlain, kScanFusedDt) and are broadcast-read.  Each thread leaves its un-gated y for
 // the chunk in shared memory; a vectorised chunk epilogue then either parks the partial in y (the other direction
 // has not reached that position yet) or adds the other direction's parked partial, applies SiLU(z) and stores the
 // final value -- 16-byte global accesses only.
@@ -30,9 +31,10 @@
 // (d) the main loop advances in blocks of 8 steps whose shared-memory stores are deferred to the end of the block, so
 //     the scheduler overlaps one step's tail with the next step's loads (and the state-register copies of a 1-step
 //     loop disappear);
-// (e) every instruction outside the main loop counts (the kernel issues at ~0.65 IPC): loads are TMA, the B|C
-//     conversion is one 4-value group per thread, the epilogue and the prefetch of parked partials have branch-free
-//     block-uniform fast paths;
+// (e) every instruction outside the main loop counts (the kernel issues at ~0.65 IPC): loads are TMA issued behind
+//     elect.sync (the six UTMALDG back to back), the forward's mode has no B|C conversion pass and ONE block barrier per
+//     chunk, the epilogue and the prefetch of parked partials have branch-free block-uniform fast paths;
+// (f) optionally (kScanFusedDt) dt_proj itself runs in the kernel on tcgen05, delta going TMEM -> registers.
 // Built, measured and removed (profiles/r01_scan_step_ub.txt): FMA-pipe polynomial exponentials for part of the 8 pairs
 // (packed FFMA2 with three distinct operands runs at ~2.7 cycles, so a polynomial pair costs more issue/FMA time than the
 // MUFU time it frees: 5.11 / 5.33 ms with 1 / 2 of 8 pairs against 5.08), whole-warp polynomial flavours, a
