@@ -134,10 +134,8 @@ class CharDNATokenizer:
     def windows_to_ascii(self, seqs: Iterable[str], length: int) -> np.ndarray:
         """Pack equal-length windows into a uint8 [n, length] ASCII matrix (the engine's host input)."""
         seqs = list(seqs)
-        buf = np.empty((len(seqs), length), dtype=np.uint8)
-        for i, s in enumerate(seqs):
-            b = s.encode("latin-1", errors="replace")
-            if len(b) != length:
-                raise ValueError(f"window {i} has length {len(b)}, expected {length}")
-            buf[i] = np.frombuffer(b, dtype=np.uint8)
-        return buf
+        for i, q in enumerate(seqs):
+            if len(q) != length:
+                raise ValueError(f"window {i} has length {len(q)}, expected {length}")
+        flat = "".join(seqs).encode("latin-1", errors="replace")     # one character -> one byte
+        return np.frombuffer(flat, dtype=np.uint8).reshape(len(seqs), length).copy()

@@ -58,18 +58,20 @@ def parse_args(argv: Optional[Sequence[str]] = None):
 class SequenceDataset:
     """Windows as a uint8 ASCII matrix.  ``__getitem__`` keeps the reference's record layout
     (``{'sequence', 'input_ids'}`` with position tokenIdx masked, :49-62) for callers that index it; the
-    scorer itself consumes whole ``ascii_batch`` slices and tokenises on the device."""
+    scorer itself consumes whole ``ascii_batch`` slices and tokenises on the device.  ``sequences`` is a list of
+    strings (possibly ragged, as the reference's table may be) or an already packed uint8 ``[n, L]`` matrix."""
 
-    def __init__(self, sequences: Sequence[str], tokenizer: CharDNATokenizer, tokenIdx: int):
-        self.sequences = list(sequences)
+    def __init__(self, sequences, tokenizer: CharDNATokenizer, tokenIdx: int):
+        self.matrix = sequences if isinstance(sequences, np.ndarray) else None
+        self.sequences = None if self.matrix is not None else list(sequences)
         self.tokenizer = tokenizer
         self.tokenIdx = tokenIdx
 
     def __len__(self):
-        return len(self.sequences)
+        return len(self.matrix) if self.matrix is not None else len(self.sequences)
 
     def __getitem__(self, idx):
-        seq = self.sequences[idx]
+        seq = bytes(self.matrix[idx]).decode("latin-1") if self.matrix is not None else self.sequences[idx]
         ids = self.tokenizer.encode_plus(seq, return_tensors="pt", return_attention_mask=False,
                                          return_token_type_ids=False)["input_ids"]
         ids[0, self.tokenIdx] = self.tokenizer.mask_token_id
@@ -77,6 +79,10 @@ class SequenceDataset:
 
     def ascii_batches(self, batch_size: int):
         """Yields (start, uint8 [b, L]) over runs of equal-length windows, in input order."""
+        if self.matrix is not None:
+            for i in range(0, len(self.matrix), batch_size):
+                yield i, self.matrix[i:i + batch_size]
+            return
         i, n = 0, len(self.sequences)
         while i < n:
             L = len(self.sequences[i])
@@ -147,8 +153,18 @@ def extract_logits(model, dataloader, device, tokenIdx, tokenizer) -> np.ndarray
 
 
 def _allele_index(values) -> np.ndarray:
-    lut = {n: i for i, n in enumerate(gio.NUCLEOTIDES)}
-    return np.array([lut[v] for v in values], dtype=np.int64)
+    """Index into A,C,G,T of every (single upper-case letter) allele; anything else is a KeyError, as in the
+    reference's ``nucleotides.index`` / column lookup (:127-133)."""
+    values = list(values)
+    flat = np.frombuffer("".join(values).encode("latin-1", errors="replace"), dtype=np.uint8)
+    if len(flat) != len(values):
+        raise KeyError(next(v for v in values if len(v) != 1))
+    lut = np.full(256, -1, dtype=np.int64)
+    lut[[ord(c) for c in gio.NUCLEOTIDES]] = np.arange(4)
+    idx = lut[flat]
+    if (idx < 0).any():
+        raise KeyError(values[int(np.flatnonzero(idx < 0)[0])])
+    return idx
 
 
 def zero_shot_score(snpDF, logits) -> List[float]:
@@ -175,35 +191,44 @@ def seq_from_vcf(args) -> Tuple[np.ndarray, List[int], list, list]:
 
 def variants_from_vcf(args):
     """Rank 0's parse of the VCF + FASTA (reference :172-214) into coordinates instead of windows: returns
-    (chrom names, {name: bytes}, chrom_id int32 [n], pos0 int64 [n], record indices, header, records) for the records
-    that carry at least one SNV ALT.  The windows are cut on the device from the resident chromosome with the same
-    slice-and-pad rule (pcad_extract_windows)."""
+    (chrom names, {name: bytes}, chrom_id int32 [n], pos0 int64 [n], record indices int64 [n], header, VcfTable) for the
+    records that carry at least one SNV ALT.  The VCF is parsed column-wise (``genome_io.read_vcf_table``: seconds for
+    10 M records); the windows are cut on the device from the resident chromosome with the same slice-and-pad rule
+    (pcad_extract_windows)."""
     logging.info(f"Reading input data from {args.inputVCF}")
     fasta = gio.read_fasta(args.inputFasta)
-    header, records = gio.read_vcf(args.inputVCF)
-    names: List[str] = []
-    index = {}
-    chrom_id, pos0, record_indices = [], [], []
-    for rec in records:
-        if not rec.has_snv:
-            continue
-        if rec.chrom not in fasta:
-            print(f"VCF record {rec.index}: chromosome {rec.chrom!r} is not in the FASTA (check that chromosome names match)")
+    table = gio.read_vcf_table(args.inputVCF)
+    record_indices = np.flatnonzero(table.has_snv).astype(np.int64)
+    cid = table.chrom_id[record_indices]
+    # chromosomes that carry scored records, in order of first appearance
+    first_seen = {}
+    if len(cid):
+        uniq, first = np.unique(cid, return_index=True)
+        first_seen = {int(u): int(f) for u, f in zip(uniq, first)}
+    used = sorted(first_seen, key=first_seen.get)
+    for c in used:
+        if table.chrom_names[c] not in fasta:
+            print(f"VCF record {int(record_indices[first_seen[c]])}: chromosome {table.chrom_names[c]!r} is not in the FASTA "
+                  f"(check that chromosome names match)")
             print("Check that VCF file is sorted and chromosome names match FASTA file.")
             raise SystemExit(1)
-        if rec.chrom not in index:
-            index[rec.chrom] = len(names)
-            names.append(rec.chrom)
-        chrom_id.append(index[rec.chrom])
-        pos0.append(rec.pos - 1)
-        record_indices.append(rec.index)
+    remap = np.full(max(len(table.chrom_names), 1), -1, dtype=np.int32)
+    remap[used] = np.arange(len(used), dtype=np.int32)
+    names = [table.chrom_names[c] for c in used]
     seqs = {c: fasta[c] for c in names}
-    return names, seqs, np.asarray(chrom_id, dtype=np.int32), np.asarray(pos0, dtype=np.int64), record_indices, header, records
+    chrom_id = remap[cid] if len(cid) else np.zeros(0, dtype=np.int32)
+    pos0 = (table.pos[record_indices] - 1).astype(np.int64)
+    return names, seqs, chrom_id.astype(np.int32), pos0, record_indices, table.header, table
 
 
 def zero_shot_score_vcf(args, recordIndices, logits, header, records):
+    """Writes the scored VCF (reference :137-169).  ``records`` is the ``VcfTable`` of ``variants_from_vcf`` or the
+    ``VcfRecord`` list of ``seq_from_vcf``."""
     logging.info("Calculating zero-shot scores")
-    gio.write_scored_vcf(args.output, header, records, recordIndices, logits)
+    if isinstance(records, gio.VcfTable):
+        gio.write_scored_vcf_table(args.output, records, recordIndices, logits)
+    else:
+        gio.write_scored_vcf(args.output, header, records, recordIndices, logits)
 
 
 def main(argv: Optional[Sequence[str]] = None):
@@ -245,7 +270,7 @@ def main(argv: Optional[Sequence[str]] = None):
             mine, n_total = ragged[0][lo:hi], len(ragged[0])
         else:
             shard = sharding.scatter_rows(windows, device=torch.device(device)) if world > 1 else windows
-            mine = [bytes(r).decode("latin-1") for r in shard.cpu().numpy()]
+            mine = np.ascontiguousarray(shard.cpu().numpy())
             n_meta = [len(windows) if rank == 0 else None]
             if world > 1:
                 torch.distributed.broadcast_object_list(n_meta, src=0)
