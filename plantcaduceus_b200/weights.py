@@ -121,3 +121,44 @@ def count_parameters(sd: Dict[str, torch.Tensor]) -> int:
         seen.add(p)
         total += v.numel()
     return total
+
+
+def write_checkpoint_dir(path: str, cfg: CaduceusConfig, sd: Dict[str, torch.Tensor], vocab=None) -> None:
+    """Writes a directory laid out like an HF-hub Caduceus snapshot (what ``save_pretrained`` leaves and what the
+    reference loads at src/zero_shot_score.py:91,96): ``config.json`` (string-keyed ``complement_map``, nested
+    ``ssm_cfg``), ``model.safetensors`` with tied tensors de-duplicated and the RCPS modules' int64 ``complement_map``
+    buffers, ``tokenizer.json`` / ``tokenizer_config.json``.  Used by the checkpoint-directory tests and by
+    tools/readme_benchmark.py (no hub checkpoint is reachable offline)."""
+    import json
+    import os
+
+    from safetensors.torch import save_file
+    os.makedirs(path, exist_ok=True)
+    d = cfg.to_dict()
+    d["architectures"] = ["CaduceusForMaskedLM"]
+    d["auto_map"] = {"AutoConfig": "configuration_caduceus.CaduceusConfig",
+                     "AutoModelForMaskedLM": "modeling_caduceus.CaduceusForMaskedLM"}
+    d["torch_dtype"] = "float32"
+    d["transformers_version"] = "4.40.0"
+    d["initializer_cfg"] = {"initializer_range": 0.02, "rescale_prenorm_residual": True, "n_residuals_per_layer": 1}
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(d, f)
+    out = {}
+    comp = torch.tensor([cfg.complement_map[i] for i in range(cfg.vocab_size)], dtype=torch.int64)
+    out["caduceus.backbone.embeddings.word_embeddings.complement_map"] = comp.clone()
+    out["lm_head.complement_map"] = comp.clone()
+    for k, v in sd.items():
+        if k == HEAD_KEY:
+            continue                       # tied to the embedding: de-duplicated on save
+        out[k] = v.clone().contiguous()
+    for i in range(cfg.n_layer):           # tied in/out projections: only one of the two names survives de-duplication
+        drop = "mamba_rev" if i % 2 == 0 else "mamba_fwd"
+        for leaf in SHARED:
+            del out[layer_key(i, drop, leaf)]
+    save_file(out, os.path.join(path, "model.safetensors"))
+    vocab = vocab or {"[PAD]": 0, "[MASK]": 1, "[UNK]": 2, "a": 3, "c": 4, "g": 5, "t": 6}
+    with open(os.path.join(path, "tokenizer.json"), "w") as f:
+        json.dump({"version": "1.0", "model": {"type": "WordLevel", "vocab": vocab, "unk_token": "[UNK]"},
+                   "normalizer": {"type": "Lowercase"}}, f)
+    with open(os.path.join(path, "tokenizer_config.json"), "w") as f:
+        json.dump({"mask_token": "[MASK]", "pad_token": "[PAD]", "unk_token": "[UNK]"}, f)

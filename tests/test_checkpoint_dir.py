@@ -14,38 +14,15 @@ from plantcaduceus_b200.weights import EMB_KEY, HEAD_KEY, layer_key
 
 
 def write_checkpoint_dir(path, cfg, sd, vocab=None):
-    """A directory laid out like an HF-hub Caduceus snapshot."""
-    from safetensors.torch import save_file
-    os.makedirs(path, exist_ok=True)
-    d = cfg.to_dict()
-    d["architectures"] = ["CaduceusForMaskedLM"]
-    d["auto_map"] = {"AutoConfig": "configuration_caduceus.CaduceusConfig",
-                     "AutoModelForMaskedLM": "modeling_caduceus.CaduceusForMaskedLM"}
-    d["torch_dtype"] = "float32"
-    d["transformers_version"] = "4.40.0"
-    d["initializer_cfg"] = {"initializer_range": 0.02, "rescale_prenorm_residual": True, "n_residuals_per_layer": 1}
-    with open(os.path.join(path, "config.json"), "w") as f:
-        json.dump(d, f)
+    """A directory laid out like an HF-hub Caduceus snapshot (plantcaduceus_b200.weights.write_checkpoint_dir)."""
+    from plantcaduceus_b200.weights import write_checkpoint_dir as w
+    w(path, cfg, sd, vocab)
     assert all(isinstance(k, str) for k in json.load(open(os.path.join(path, "config.json")))["complement_map"])
-    out = {}
-    comp = torch.tensor([cfg.complement_map[i] for i in range(cfg.vocab_size)], dtype=torch.int64)
-    out["caduceus.backbone.embeddings.word_embeddings.complement_map"] = comp.clone()
-    out["lm_head.complement_map"] = comp.clone()
-    for k, v in sd.items():
-        if k == HEAD_KEY:
-            continue                       # tied to the embedding: de-duplicated on save
-        out[k] = v.clone().contiguous()
-    for i in range(cfg.n_layer):           # tied in/out projections: only one of the two names survives de-duplication
-        drop = "mamba_rev" if i % 2 == 0 else "mamba_fwd"
-        for leaf in ("in_proj.weight", "out_proj.weight"):
-            del out[layer_key(i, drop, leaf)]
-    save_file(out, os.path.join(path, "model.safetensors"))
-    vocab = vocab or {"[PAD]": 0, "[MASK]": 1, "[UNK]": 2, "a": 3, "c": 4, "g": 5, "t": 6}
-    with open(os.path.join(path, "tokenizer.json"), "w") as f:
-        json.dump({"version": "1.0", "model": {"type": "WordLevel", "vocab": vocab, "unk_token": "[UNK]"},
-                   "normalizer": {"type": "Lowercase"}}, f)
-    with open(os.path.join(path, "tokenizer_config.json"), "w") as f:
-        json.dump({"mask_token": "[MASK]", "pad_token": "[PAD]", "unk_token": "[UNK]"}, f)
+    from safetensors import safe_open
+    with safe_open(os.path.join(path, "model.safetensors"), "pt") as f:
+        keys = set(f.keys())
+    assert HEAD_KEY not in keys and "lm_head.complement_map" in keys
+    assert layer_key(0, "mamba_rev", "in_proj.weight") not in keys and layer_key(0, "mamba_fwd", "in_proj.weight") in keys
 
 
 def test_checkpoint_dir_parses_on_cpu(tmp_path):
