@@ -105,7 +105,7 @@ def _vllm_ssd(x, dt, A, Bm, Cm, D, dt_bias, chunk):
 @pytest.mark.parametrize("S,L,H,chunk", [(2, 256, 4, 64), (1, 512, 2, 128), (1, 200, 2, 64)])
 def test_ssd_scan_matches_mamba_ssm_chunk_scan_port(lib, cuda_device, S, L, H, chunk):
     """oracle.ssd_scan_ref and pcad_op_ssd_scan (fp32 sequential kernel) against the mamba_ssm-derived chunked scan.
-    The Triton kernels multiply through tl.dot (TF32 for fp32 operands), so the bar is 5e-3 of the output scale: any
+    The Triton kernels multiply through tl.dot (TF32 for fp32 operands), so the bar is 1e-2 of the output scale: any
     difference of SEMANTICS (where dt_bias / softplus / D / the decay enter) is O(1)."""
     P, N = 64, 64
     E = H * P
@@ -122,7 +122,7 @@ def test_ssd_scan_matches_mamba_ssm_chunk_scan_port(lib, cuda_device, S, L, H, c
                        for s in range(S)]).cpu()
     assert not torch.isnan(got).any()
     scale = want.abs().max().item()
-    assert (got - want).abs().max().item() <= 5e-3 * scale
+    assert (got - want).abs().max().item() <= 1e-2 * scale
     # libpcad's fp32 kernel, forward direction, against the same port (no oracle in between)
     CD = E + 2 * N
     xbc = torch.cat([x.reshape(S * L, E), Bm.reshape(S * L, N), Cm.reshape(S * L, N)], dim=1)
@@ -134,11 +134,11 @@ def test_ssd_scan_matches_mamba_ssm_chunk_scan_port(lib, cuda_device, S, L, H, c
                               ptr(y[0]), ptr(y[1]), S, L, H, F32, 1, stream())
     assert rc == 0, lib.pcad_last_error(None)
     torch.cuda.synchronize()
-    assert (y[0].cpu().reshape(S, L, H, P) - got).abs().max().item() <= 5e-3 * scale
+    assert (y[0].cpu().reshape(S, L, H, P) - got).abs().max().item() <= 1e-2 * scale
     # the reverse direction is the same scan on the flipped sequence
     got_r = torch.stack([_vllm_ssd(dev(x[s].flip(0)), dev(dt[s].flip(0)), dev(A), dev(Bm[s].flip(0)), dev(Cm[s].flip(0)),
                                    dev(D), dev(bias), chunk).flip(0) for s in range(S)]).cpu()
-    assert (y[1].cpu().reshape(S, L, H, P) - got_r).abs().max().item() <= 5e-3 * scale
+    assert (y[1].cpu().reshape(S, L, H, P) - got_r).abs().max().item() <= 1e-2 * scale
 
 
 # ---- Mamba-2 gated RMSNorm: port of mamba_ssm's layernorm_gated ----------------------------------------------------------
