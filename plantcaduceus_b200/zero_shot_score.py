@@ -241,9 +241,12 @@ def main(argv: Optional[Sequence[str]] = None):
     # One process per GPU under torchrun: contiguous variant ranges per rank, scores gathered once at the end
     # (SURVEY.md 8e); a single process otherwise.  Only rank 0 reads the input files.
     rank, local_rank, world = sharding.env_world()
-    device = f"cuda:{local_rank}" if world > 1 else args.device
+    # "-device cpu" exists for the host-logic tests only (gloo ranks, stubbed model): the engine itself has no CPU path
+    on_cpu = torch.device(args.device).type == "cpu"
+    device = args.device if (world == 1 or on_cpu) else f"cuda:{local_rank}"
     if world > 1:
-        torch.cuda.set_device(local_rank)
+        if not on_cpu:
+            torch.cuda.set_device(local_rank)
         sharding.init_process_group(device=torch.device(device))
     model, tokenizer = load_model_and_tokenizer(args.model, device, args.dtype, args.seed)
 

@@ -159,3 +159,62 @@ def test_score_variants_single_process_and_fasta_reader(tmp_path):
     fa.write_bytes(b">a\nAC\n>a\nGT\n")
     with pytest.raises(ValueError, match="duplicate"):
         gio.read_fasta(str(fa))
+
+
+def _worker_cli(rank, world, ports, tmp, q):
+    """The command line itself under two gloo ranks, GPU steps stubbed (fake engine): rank 0 alone reads the inputs,
+    windows / coordinates travel over the process group, rank 0 writes; the other rank returns without output."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(ports[0]))
+    from plantcaduceus_b200 import CharDNATokenizer
+    from plantcaduceus_b200 import genome_io as gio
+    from plantcaduceus_b200 import zero_shot_score as zss
+    tok = CharDNATokenizer()
+
+    class Engine(_FakeEngine):                       # bounded "logits", so that the scores are finite numbers
+        def score_windows_device(self, windows, token_idx, out=None):
+            res = 3 * torch.sin(super().score_windows_device(windows, token_idx))
+            return res if out is None else out.copy_(res)
+
+    zss.load_model_and_tokenizer = lambda *a, **k: (Engine(), tok)
+
+    def fake_extract_logits(model, dataloader, device, tokenIdx, tokenizer):
+        dataset, batch_size = dataloader
+        out = np.zeros((len(dataset), 4), dtype=np.float32)
+        for start, batch in dataset.ascii_batches(batch_size):
+            out[start:start + len(batch)] = 3 * np.sin(_fake_score(np.asarray(batch)))
+        return gio.softmax4(out)
+
+    zss.extract_logits = fake_extract_logits
+    gold = os.path.join(ROOT, "tests", "golden")
+    rc1 = zss.main(["-input-table", os.path.join(gold, "example_snp.tsv"), "-output", os.path.join(tmp, f"w{world}.tsv"),
+                    "-device", "cpu", "-batchSize", "32"])
+    os.environ["MASTER_PORT"] = str(ports[1])          # main() tears its process group down: a fresh rendezvous per call
+    rc2 = zss.main(["-input-vcf", os.path.join(gold, "example_maize_snp.vcf"), "-input-fasta",
+                    os.path.join(gold, "example_genome.fa.gz"), "-output", os.path.join(tmp, f"w{world}.vcf"),
+                    "-device", "cpu", "-batchSize", "32"])
+    q.put((rank, rc1 == 0 and rc2 == 0))
+
+
+def test_cli_world_size_2_equals_single_process(tmp_path):
+    """python -m plantcaduceus_b200.zero_shot_score under 2 ranks writes byte-identical files to the 1-process run
+    (table path: packed windows scattered; VCF path: coordinates + chromosomes broadcast; scores gathered once)."""
+    ctx = mp.get_context("spawn")
+    for world in (1, 2):
+        q = ctx.Queue()
+        ports = (_free_port(), _free_port())
+        procs = [ctx.Process(target=_worker_cli, args=(r, world, ports, str(tmp_path), q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(240)
+            if p.is_alive():
+                p.kill()
+            assert p.exitcode == 0
+        assert dict(q.get(timeout=10) for _ in range(world)) == {r: True for r in range(world)}
+    for ext in ("tsv", "vcf"):
+        one, two = (tmp_path / f"w1.{ext}").read_bytes(), (tmp_path / f"w2.{ext}").read_bytes()
+        assert len(one) > 1000 and one == two
+    text = (tmp_path / "w1.vcf").read_text()
+    assert text.count("plantCAD_zero_shot=") == 190 and "inf" not in text and "nan" not in text
