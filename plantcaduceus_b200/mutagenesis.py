@@ -72,12 +72,17 @@ def write_candidate_vcf(path: str, chrom_name: str, result, scores: bool = False
     """The headerless 7-column rows ``1_simulation.R:100-120`` writes (chr, pos, '.', ref, alt, '.', '.'), one per
     (position, alt); with ``scores=True`` an eighth INFO column carries ``plantCAD_zero_shot=<score>`` as
     ``zero_shot_score.py -input-vcf`` would add it."""
+    pos = np.asarray(result["pos"]).astype(np.int64).astype(str).tolist()
+    ref = np.asarray(result["ref"], dtype=np.uint8).tobytes().decode("latin-1")
+    alt = np.asarray(result["alt"], dtype=np.uint8).tobytes().decode("latin-1")
+    head = chrom_name + "\t"
+    if scores:
+        sc = np.asarray(result["score"], dtype=np.float32).astype(str).tolist()        # str(np.float32(x)), vectorised
+        rows = [f"{head}{p}\t.\t{r}\t{a}\t.\t.\tplantCAD_zero_shot={v}\n" for p, r, a, v in zip(pos, ref, alt, sc)]
+    else:
+        rows = [f"{head}{p}\t.\t{r}\t{a}\t.\t.\n" for p, r, a in zip(pos, ref, alt)]
     with open(path, "w") as f:
-        for k in range(len(result["pos"])):
-            row = [chrom_name, str(int(result["pos"][k])), ".", chr(int(result["ref"][k])), chr(int(result["alt"][k])), ".", "."]
-            if scores:
-                row.append(f"plantCAD_zero_shot={np.float32(result['score'][k])}")
-            f.write("\t".join(row) + "\n")
+        f.write("".join(rows))
 
 
 def saturation_mutagenesis(model, window: str, positions: Optional[Sequence[int]] = None, batch_size: int = 256):
