@@ -73,11 +73,10 @@ class CaduceusForMaskedLM:
                 sd = load_file(st)
             else:
                 sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu", weights_only=True)
-            # safetensors checkpoints are saved with tied tensors de-duplicated: restore the embedding <-> LM head tie
-            # (the mamba_fwd / mamba_rev projection tie is resolved by the engine, whichever name survived)
-            from .weights import EMB_KEY, HEAD_KEY
-            if EMB_KEY not in sd and HEAD_KEY in sd:
-                sd[EMB_KEY] = sd[HEAD_KEY]
+            # safetensors checkpoints are saved with tied tensors de-duplicated: restore both names of every tie, as HF's
+            # tie_weights does after loading (embedding <-> LM head, mamba_fwd <-> mamba_rev in/out projections)
+            from .weights import restore_tied_names
+            restore_tied_names(sd, cfg.n_layer)
             return cls(cfg, sd, torch_dtype, CharDNATokenizer.from_pretrained(path))
         raise FileNotFoundError(
             f"{path!r} is not a local checkpoint directory (no network here). Use from_random('{path}') for "

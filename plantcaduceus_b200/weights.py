@@ -123,6 +123,25 @@ def count_parameters(sd: Dict[str, torch.Tensor]) -> int:
     return total
 
 
+def restore_tied_names(sd: Dict[str, torch.Tensor], n_layer: int) -> Dict[str, torch.Tensor]:
+    """A checkpoint saved with tied tensors de-duplicated carries one name per tie; after loading, HF's ``tie_weights``
+    makes both names resolve to the same tensor again.  Does the same in place: embedding <-> LM head, and
+    ``mamba_fwd`` <-> ``mamba_rev`` for ``in_proj.weight`` / ``out_proj.weight`` (bidirectional_weight_tie)."""
+    for a, b in ((EMB_KEY, HEAD_KEY),):
+        if a not in sd and b in sd:
+            sd[a] = sd[b]
+        elif b not in sd and a in sd:
+            sd[b] = sd[a]
+    for i in range(n_layer):
+        for leaf in SHARED:
+            f, r = layer_key(i, "mamba_fwd", leaf), layer_key(i, "mamba_rev", leaf)
+            if f not in sd and r in sd:
+                sd[f] = sd[r]
+            elif r not in sd and f in sd:
+                sd[r] = sd[f]
+    return sd
+
+
 def write_checkpoint_dir(path: str, cfg: CaduceusConfig, sd: Dict[str, torch.Tensor], vocab=None) -> None:
     """Writes a directory laid out like an HF-hub Caduceus snapshot (what ``save_pretrained`` leaves and what the
     reference loads at src/zero_shot_score.py:91,96): ``config.json`` (string-keyed ``complement_map``, nested
