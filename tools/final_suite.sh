@@ -13,6 +13,8 @@ python bench.py --workload mutagenesis --cpu-sample 0 > gpurun_out/${TAG}_final_
 python bench.py --workload long --model l32 --cpu-sample 0 > gpurun_out/${TAG}_final_long_l32.json 2> /dev/null
 python bench.py --workload long --model cad2-small --cpu-sample 0 > gpurun_out/${TAG}_final_long_cad2small.json 2> /dev/null
 python bench.py --workload long --model cad2-large --batch 8 --cpu-sample 0 > gpurun_out/${TAG}_final_long_cad2large.json 2> /dev/null
+python tools/readme_benchmark.py --out gpurun_out/${TAG}_readme_benchmark.json > gpurun_out/${TAG}_readme_benchmark.log 2>&1; tail -4 gpurun_out/${TAG}_readme_benchmark.log
+python tools/cli_vcf_benchmark.py --out gpurun_out/${TAG}_cli_vcf_benchmark.json > gpurun_out/${TAG}_cli_vcf_benchmark.log 2>&1; tail -1 gpurun_out/${TAG}_cli_vcf_benchmark.log
 python tools/small_batch_probe.py > gpurun_out/${TAG}_small_batch.log 2>&1; tail -3 gpurun_out/${TAG}_small_batch.log
 B="python bench.py --steps 1 --warmup 1 --cpu-sample 0 --no-clocks"
 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 300 --csv --log-file gpurun_out/launches_${TAG}.csv $B > gpurun_out/ncu_bench.log 2>&1
