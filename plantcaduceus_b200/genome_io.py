@@ -279,11 +279,14 @@ def windows_from_vcf(records: Sequence[VcfRecord], fasta: Dict[str, bytes], toke
 # scores
 # ---------------------------------------------------------------------------------------------------
 def softmax4(logits4: np.ndarray) -> np.ndarray:
-    """softmax over the a,c,g,t logits in float32 (reference extract_logits, :119)."""
-    x = np.asarray(logits4, dtype=np.float32)
-    x = x - x.max(axis=1, keepdims=True)
-    e = np.exp(x)
-    return (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
+    """softmax over the a,c,g,t logits in float32, computed by the very call the reference makes
+    (``torch.nn.functional.softmax(logits.cpu(), dim=1).numpy()``, extract_logits :119), so that identical logits give
+    bit-identical probabilities and score strings."""
+    import torch
+    x = np.ascontiguousarray(logits4, dtype=np.float32)
+    if x.size == 0:
+        return x.reshape(-1, 4)
+    return torch.nn.functional.softmax(torch.from_numpy(x), dim=1).numpy()
 
 
 def llr(probs: np.ndarray, ref_idx: np.ndarray, alt_idx: np.ndarray) -> np.ndarray:
