@@ -17,7 +17,16 @@ structurally independent of the engine's index math.  It is pinned by:
   (2) an independent implementation of the Mamba-1 mixer that IS importable here,
       ``transformers.models.mamba.modeling_mamba.MambaMixer.slow_forward`` (tests/test_oracle.py),
   (3) parameter counts against reference README.md:60-63,
-  (4) the module tree / shapes printed at reference notebooks/examples.ipynb:61-98,132,183.
+  (4) the module tree / shapes printed at reference notebooks/examples.ipynb:61-98,132,183,
+  (5) on the GPU box, code that descends from the reference's own kernels (vLLM's ports of mamba_ssm's selective_scan_fwd,
+      mamba_chunk_scan_combined and layernorm_gated; flash_attn's rms_norm_fn, the file mamba_ssm's layer_norm.py copies):
+      tests/test_thirdparty_pin_gpu.py, tests/test_thirdparty_pin2_gpu.py,
+  (6) opt-in, the reference notebook's stored softmax output of the pretrained l20 checkpoint
+      (tests/test_reference_notebook_pin.py; needs a local snapshot of the hub checkpoint).
+What IS pinned by outputs of the reference itself: everything of the path that lives in /root/reference -- the scoring
+functions at the bottom of this file and the host path / callers they restate -- through tests/golden/reference_run/
+(the reference's zero_shot_score.py main(), seq_from_vcf, zero-shot-eval.py, train_XGBoost.extract_embeddings EXECUTED in
+the build container with this oracle as the model behind them; tests/golden/make_reference_run_golden.py).
 
 Every function cites what it follows.  "[EXT]" marks upstream code that is not in /root/reference.
 """
