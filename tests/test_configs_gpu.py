@@ -156,13 +156,13 @@ def test_scan_region_equals_cli_on_the_vcf_it_emits(cuda_device, tmp_path):
     """Region-level saturation mutagenesis with the reference pipeline's semantics (1_simulation.R:85-120 ->
     zero_shot_score.py -input-vcf): every A/C/G/T position of the region gets its own centred window.  The scores equal,
     bit for bit, what the drop-in CLI writes for the headerless VCF rows the scan emits (one forward per ROW there, one per
-    position here), including positions whose window is N-padded at the chromosome start and soft-masked / N bases that
-    the R script drops."""
+    position here), including positions whose window is N-padded at the chromosome start, soft-masked bases (mutated, with
+    an upper-case ref: the R script's genome went through Biostrings) and N bases (dropped)."""
     from plantcaduceus_b200 import mutagenesis as mut, zero_shot_score as zs
     from plantcaduceus_b200.modeling import CaduceusForMaskedLM
     rng = np.random.default_rng(17)
     chrom = bytearray(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=1400).tobytes())
-    chrom[30:34] = b"acgt"      # soft-masked: dropped by `ref %in% c("A","C","G","T")`
+    chrom[30:34] = b"acgt"      # soft-masked: Biostrings has no lower case, so these are A, C, G, T to the R script
     chrom[50] = ord("N")
     chrom = bytes(chrom)
     fasta = tmp_path / "genome.fa"
@@ -170,11 +170,11 @@ def test_scan_region_equals_cli_on_the_vcf_it_emits(cuda_device, tmp_path):
     cfg = CaduceusConfig(d_model=128, n_layer=2)
     ckpt_model = CaduceusForMaskedLM.from_random(cfg, seed=0, torch_dtype=torch.float32).to(cuda_device)
     res = mut.scan_region(ckpt_model, chrom, 20, 139, batch_size=50)
-    n_pos = 120 - 4 - 1
+    n_pos = 120 - 1
     assert len(res["positions"]) == n_pos and len(res["pos"]) == 3 * n_pos
     assert res["pos"].tolist() == sorted(res["pos"].tolist())
     assert all(r != a for r, a in zip(res["ref"], res["alt"]))
-    assert 31 not in res["positions"] and 51 not in res["positions"]
+    assert 51 not in res["positions"] and [chr(c) for c in res["ref"][res["pos"] == 31]] == ["A"] * 3
     vcf_in, vcf_out = str(tmp_path / "cand.vcf"), str(tmp_path / "scored.vcf")
     mut.write_candidate_vcf(vcf_in, "chrT", res)
     first = open(vcf_in).readline().rstrip("\n").split("\t")

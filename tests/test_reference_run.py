@@ -234,3 +234,54 @@ def test_fire_style_argument_parsing():
     assert zse.main([]) == 2 and zse.main(["nope"]) == 2 and zse.main(["evo_cons", "--bogus", "1"]) == 2
     with pytest.raises(RuntimeError, match="CUDA is required"):
         zse._require_cuda("cpu")
+
+
+# ---- in-silico mutagenesis front end (pipelines/in-silico-mutagenesis/1_simulation.R; R is not installed: literal restatement) ----
+def _r_script_rows(chrom: str, regions):
+    """1_simulation.R:85-100 spelled out: per region the positions and bases (Biostrings: upper case), rbind, keep A/C/G/T,
+    crossing() with the alts (de-duplicates and sorts), drop ref == alt, arrange(pos)."""
+    rows = set()
+    for s, e in regions:
+        for p in range(s, e + 1):
+            ref = chrom[p - 1].upper()
+            if ref in "ACGT":
+                for alt in "ACGT":
+                    if alt != ref:
+                        rows.add((p, ref, alt))
+    return sorted(rows)
+
+
+def test_mutagenesis_front_end_matches_r_script_semantics(tmp_path, monkeypatch, cpu_engine):
+    from plantcaduceus_b200 import mutagenesis as mut
+    rng = np.random.default_rng(23)
+    chrom = "".join(rng.choice(list("ACGTacgtNRY"), size=900, p=[0.2, 0.2, 0.2, 0.2, 0.04, 0.04, 0.04, 0.04, 0.02, 0.01, 0.01]))
+    other = "ACGT" * 50
+    (tmp_path / "g.fa").write_text(">chrA x\n" + "\n".join(chrom[i:i + 70] for i in range(0, 900, 70)) + "\n>chrB\n" + other + "\n")
+    gff = ["##gff-version 3", "chrA\tsrc\tgene\t120\t140\t.\t+\t.\tID=g1", "chrA\tsrc\tmRNA\t120\t140\t.\t+\t.\tID=m1;Parent=g1",
+           "chrA\tsrc\texon\t125\t135\t.\t+\t.\tParent=m1", "chrA\tsrc\tgene\t135\t160\t.\t-\t.\tID=g2",      # overlaps g1 once extended
+           "chrA\tsrc\tgene\t5\t30\t.\t+\t.\tID=g3",                                                           # 5 - 10 < 1: dropped
+           "chrA\tsrc\tgene\t880\t895\t.\t+\t.\tID=g4",                                                        # 895 + 10 > 900: dropped
+           "chrB\tsrc\tgene\t50\t60\t.\t+\t.\tID=g5", "chrA\tsrc\tgene\t600\t610\t.\t+\t.\tID=g6", "##FASTA", ">chrA", "ACGT"]
+    (tmp_path / "a.gff").write_text("\n".join(gff) + "\n")
+    regions = mut.gene_regions_from_gff(str(tmp_path / "a.gff"), "chrA", flank=10, chrom_len=900)
+    assert regions == [(110, 150), (125, 170), (590, 620)]
+    assert mut.merge_regions(regions) == [(110, 170), (590, 620)]
+    want = _r_script_rows(chrom, regions)
+    got = mut.enumerate_candidates(chrom.encode(), regions)
+    assert list(zip(got["pos"].tolist(), map(chr, got["ref"]), map(chr, got["alt"]))) == want
+    # the command line without --score == the R script's output file
+    assert mut.main(["-g", str(tmp_path / "a.gff"), "-f", str(tmp_path / "g.fa"), "-o", str(tmp_path / "cand.vcf"), "-c", "chrA", "-k", "10"]) == 0
+    assert (tmp_path / "cand.vcf").read_text() == "".join(f"chrA\t{p}\t.\t{r}\t{a}\t.\t.\n" for p, r, a in want)
+    assert mut.main(["-g", str(tmp_path / "a.gff"), "-f", str(tmp_path / "g.fa"), "-o", str(tmp_path / "x.vcf"), "-c", "chrZ"]) == 1
+    # scored in the same run == the candidate file pushed through the scoring command line (README.md:56-64 of the pipeline)
+    res = mut.scan_regions(cpu_engine, chrom.encode(), regions, batch_size=64, length=512)
+    assert list(zip(res["pos"].tolist(), map(chr, res["ref"]), map(chr, res["alt"]))) == want
+    _patch_cli(monkeypatch, cpu_engine)
+    assert zss.main(["-input-vcf", str(tmp_path / "cand.vcf"), "-input-fasta", str(tmp_path / "g.fa"), "-output", str(tmp_path / "s.vcf"),
+                     "-device", "cpu", "-batchSize", "64"]) == 0
+    rows = [ln.rstrip("\n").split("\t") for ln in open(tmp_path / "s.vcf") if not ln.startswith("#")]
+    assert len(rows) == len(want)
+    cli = np.array([np.float32(r[7].split("plantCAD_zero_shot=")[1]) for r in rows])
+    assert np.allclose(cli, res["score"], rtol=0, atol=3e-6)          # one forward per row there, per position here (batching)
+    mut.write_candidate_vcf(str(tmp_path / "scored.vcf"), "chrA", res, scores=True)
+    assert sum(1 for _ in open(tmp_path / "scored.vcf")) == len(want)
