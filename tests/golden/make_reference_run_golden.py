@@ -203,10 +203,39 @@ def tiny_model():
     return OracleModel(), CharDNATokenizer()
 
 
+def config1(zss):
+    """BASELINE.json configs[0] through the reference's main(): PlantCaduceus_l20 random-init seed 0 (the oracle, fp32) on
+    examples/example_snp.tsv -> config1_table_scores.tsv (about ten minutes of CPU)."""
+    from oracle import caduceus_oracle as O
+    from plantcaduceus_b200 import CharDNATokenizer, preset, random_init_state_dict
+    cfg = preset("PlantCaduceus_l20")
+    sd = random_init_state_dict(cfg, seed=0)
+
+    class L20:
+        def to(self, *a, **k):
+            return self
+
+        def eval(self):
+            return self
+
+        def __call__(self, input_ids=None, **_kw):
+            with torch.inference_mode():
+                logits, _ = O.caduceus_forward(sd, cfg, input_ids, dtype=torch.float32)
+            return SimpleNamespace(logits=logits)
+
+    zss.load_model_and_tokenizer = lambda model_dir, device: (L20(), CharDNATokenizer())
+    sys.argv = ["zero_shot_score.py", "-input-table", os.path.join(HERE, "example_snp.tsv"), "-output",
+                os.path.join(OUT, "config1_table_scores.tsv"), "-model", "unused", "-device", "cpu", "-batchSize", "37"]
+    zss.main()
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     _install_stubs()
     zss = _load(os.path.join(REF, "src", "zero_shot_score.py"), "ref_zero_shot_score")
+    if "--config1" in sys.argv:
+        config1(zss)
+        return
     zse = _load(os.path.join(REF, "src", "zero-shot-eval.py"), "ref_zero_shot_eval")
     txg = _load(os.path.join(REF, "src", "train_XGBoost.py"), "ref_train_xgboost")
     model, tok = tiny_model()
