@@ -72,8 +72,14 @@ class CharDNATokenizer:
                 with open(p) as f:
                     tj = json.load(f)
                 vocab = tj.get("model", {}).get("vocab")
+                if isinstance(vocab, list):         # Unigram-style [[token, score], ...]: the id is the list index
+                    vocab = {(e[0] if isinstance(e, (list, tuple)) else e): i for i, e in enumerate(vocab)}
                 if isinstance(vocab, dict):
-                    return cls(vocab={k: int(v) for k, v in vocab.items()})
+                    vocab = {k: int(v) for k, v in vocab.items()}
+                    for t in tj.get("added_tokens") or []:      # special tokens may live only here
+                        if isinstance(t, dict) and "content" in t and "id" in t:
+                            vocab.setdefault(t["content"], int(t["id"]))
+                    return cls(vocab=vocab)
             p = os.path.join(str(name_or_path), "vocab.json")
             if os.path.exists(p):
                 with open(p) as f:

@@ -111,3 +111,22 @@ def test_out_of_range_ids_raise(cuda_device):
         m.score_masked(u8, torch.zeros((2, 1), dtype=torch.int32))
     ok = m.score_masked(torch.full((2, 16), 4, dtype=torch.uint8), torch.zeros((2, 1), dtype=torch.int32))
     assert torch.isfinite(ok).all()
+
+
+def test_tokenizer_json_variants(tmp_path):
+    """tokenizer.json as the `tokenizers` library writes it: special tokens possibly only under ``added_tokens``; a
+    list-style vocabulary."""
+    d = tmp_path / "a"
+    d.mkdir()
+    (d / "tokenizer.json").write_text(json.dumps({
+        "added_tokens": [{"id": 0, "content": "[PAD]", "special": True}, {"id": 1, "content": "[MASK]", "special": True},
+                         {"id": 2, "content": "[UNK]", "special": True}],
+        "model": {"type": "WordLevel", "vocab": {"a": 3, "c": 4, "g": 5, "t": 6}, "unk_token": "[UNK]"}}))
+    tok = CharDNATokenizer.from_pretrained(str(d))
+    assert (tok.pad_token_id, tok.mask_token_id, tok.unk_token_id) == (0, 1, 2) and tok.encode("ACGTN") == [3, 4, 5, 6, 2]
+    e = tmp_path / "b"
+    e.mkdir()
+    (e / "tokenizer.json").write_text(json.dumps({"model": {"type": "Unigram", "vocab": [["[PAD]", 0.0], ["[MASK]", 0.0], ["[UNK]", 0.0],
+                                                                                          ["t", -1.0], ["g", -1.0], ["c", -1.0], ["a", -1.0]]}}))
+    tok = CharDNATokenizer.from_pretrained(str(e))
+    assert tok.encode("acgt") == [6, 5, 4, 3] and tok.mask_token_id == 1
