@@ -285,3 +285,14 @@ def test_mutagenesis_front_end_matches_r_script_semantics(tmp_path, monkeypatch,
     assert np.allclose(cli, res["score"], rtol=0, atol=3e-6)          # one forward per row there, per position here (batching)
     mut.write_candidate_vcf(str(tmp_path / "scored.vcf"), "chrA", res, scores=True)
     assert sum(1 for _ in open(tmp_path / "scored.vcf")) == len(want)
+
+
+def test_config1_golden_is_what_the_reference_main_writes():
+    """BASELINE.json configs[0]: the committed oracle vectors (tests/golden/l20_seed0_example_scores.npz, which the GPU command
+    line is compared with in tests/test_scoring_cli_gpu.py) equal, as float32, the zeroShotScore column the reference's own
+    main() wrote for the same model (reference_run/config1_scores.tsv, `make_reference_run_golden.py --config1`)."""
+    g = np.load(os.path.join(GOLD, "l20_seed0_example_scores.npz"))
+    df = pd.read_csv(os.path.join(RUN, "config1_scores.tsv"), sep="\t")
+    src = pd.read_csv(os.path.join(GOLD, "example_snp.tsv"), sep="\t").iloc[g["rows"]]
+    assert len(df) == 185 and df["pos"].tolist() == src["pos"].tolist() and df["alt"].tolist() == src["alt"].tolist()
+    assert np.array_equal(df["zeroShotScore"].to_numpy().astype(np.float32), g["llr"].astype(np.float32))
