@@ -183,3 +183,82 @@ def test_plantcad2_parameter_counts(name, millions):
     assert round(n128 / 1e6) != millions
     if "Small" in name:
         assert count_parameters(random_init_state_dict(cfg, 0)) == n
+
+
+# ---- the plain-C restatement of the byte / integer rules (oracle/host_rules.c) -----------------------------------------
+def _host_rules():
+    import ctypes as C
+    import __graft_entry__ as entry
+    lib = C.CDLL(entry.build_oracle())
+    lib.pcad_oracle_extract_window.restype = C.c_int
+    return lib, C
+
+
+def test_c_oracle_windows_equal_reference_seq_from_vcf_and_host_rule():
+    """oracle/host_rules.c::pcad_oracle_extract_window against (1) the windows the REFERENCE'S seq_from_vcf returned
+    (tests/golden/reference_run/: example VCF, and a small genome with soft-masked / N bases at four tokenIdx values),
+    (2) plantcaduceus_b200.genome_io.extract_window on random positions and chromosome lengths."""
+    import json
+    import os
+    import numpy as np
+    from plantcaduceus_b200 import genome_io as gio
+    lib, C = _host_rules()
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+    def c_window(chrom: bytes, pos0: int, tidx: int, L: int = 512) -> bytes:
+        out = (C.c_uint8 * L)()
+        buf = (C.c_uint8 * max(len(chrom), 1)).from_buffer_copy(chrom or b"\0")
+        lib.pcad_oracle_extract_window(buf, C.c_int64(len(chrom)), C.c_int64(pos0), tidx, L, out)
+        return bytes(out)
+
+    fasta = gio.read_fasta(os.path.join(gold, "reference_run", "small_genome.fa"))
+    recs = gio.read_vcf(os.path.join(gold, "reference_run", "small.vcf"))[1]
+    with open(os.path.join(gold, "reference_run", "small_windows.json")) as f:
+        small = json.load(f)
+    for tidx, want in small.items():
+        got = [c_window(fasta[recs[i].chrom], recs[i].pos - 1, int(tidx)).decode() for i in want["record_indices"]]
+        assert got == want["windows"], f"tokenIdx {tidx}"
+    g = np.load(os.path.join(gold, "reference_run", "vcf_windows.npz"))
+    fasta = gio.read_fasta(os.path.join(gold, "example_genome.fa.gz"))
+    recs = gio.read_vcf(os.path.join(gold, "example_maize_snp.vcf"))[1]
+    for k in range(0, len(g["record_indices"]), 7):
+        r = recs[int(g["record_indices"][k])]
+        assert c_window(fasta[r.chrom], r.pos - 1, 255) == bytes(g["windows"][k])
+    rng = np.random.default_rng(4)
+    for _ in range(300):
+        n = int(rng.integers(1, 1500))
+        chrom = bytes(rng.choice(np.frombuffer(b"ACGTacgtN", dtype=np.uint8), size=n))
+        pos0, tidx = int(rng.integers(0, n)), int(rng.integers(0, 512))
+        assert c_window(chrom, pos0, tidx) == gio.extract_window(chrom, pos0, tidx, 512)
+
+
+def test_c_oracle_tokenise_rc_and_slop():
+    import os
+    import numpy as np
+    from plantcaduceus_b200 import CharDNATokenizer
+    lib, C = _host_rules()
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    tok = CharDNATokenizer()
+    rows = [ln.rstrip("\n").split("\t")[6] for ln in open(os.path.join(gold, "example_snp.tsv"))][1:]
+    ascii_mat = np.frombuffer("".join(rows).encode(), dtype=np.uint8).copy()
+    ids = np.zeros_like(ascii_mat)
+    p8 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint8))
+    lut = np.ascontiguousarray(tok.lut, dtype=np.uint8)
+    lib.pcad_oracle_tokenize(p8(ascii_mat), C.c_int64(ascii_mat.size), p8(lut), 512, 255, tok.mask_token_id, p8(ids))
+    assert np.array_equal(ids.reshape(-1, 512), np.load(os.path.join(gold, "example_ids.npz"))["ids"])
+    # RC strand ids == the oracle's reverse_complement_ids
+    cfg = preset("PlantCaduceus_l20")
+    comp = np.array([cfg.complement_map[i] for i in range(cfg.vocab_size)], dtype=np.uint8)
+    row = np.ascontiguousarray(ids[:512])
+    out = np.zeros(512, dtype=np.uint8)
+    lib.pcad_oracle_rc_ids(p8(row), 512, p8(comp), p8(out))
+    want = O.reverse_complement_ids(torch.from_numpy(row.astype(np.int64))[None], cfg)[0].numpy()
+    assert np.array_equal(out, want)
+    # format_VCF.sh interval == the start / end columns of the reference's example table
+    s, e = C.c_int64(), C.c_int64()
+    for ln in list(open(os.path.join(gold, "example_snp.tsv")))[1:20]:
+        f = ln.split("\t")
+        lib.pcad_oracle_slop(C.c_int64(int(f[3])), C.c_int64(10 ** 9), 255, 256, C.byref(s), C.byref(e))
+        assert (s.value, e.value) == (int(f[1]), int(f[2]))
+    lib.pcad_oracle_slop(C.c_int64(10), C.c_int64(100), 255, 256, C.byref(s), C.byref(e))
+    assert (s.value, e.value) == (0, 100)
