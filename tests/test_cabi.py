@@ -57,3 +57,18 @@ def test_no_cpu_fallback(lib):
     m = CaduceusForMaskedLM.from_random(CaduceusConfig(d_model=128, n_layer=1))
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(input_ids=torch.zeros(1, 8, dtype=torch.long))
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: no module of the package (nor the CUDA sources) may import, load or mention it, and the
+    package has no CPU fallback to route through."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "plantcaduceus_b200", "**", "*.py"), recursive=True) + \
+        glob.glob(os.path.join(root, "plantcaduceus_b200", "csrc", "*.cu*"))
+    assert len(files) > 15
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[/.](caduceus_oracle|host_rules|_build)|libhost_rules", re.M)
+    for f in files:
+        assert not pat.search(open(f, errors="ignore").read()), f
